@@ -1,0 +1,154 @@
+/*
+ * bopl_b200.h — C-ABI of the B200-native uEI hot path (libbopl_b200.so).
+ *
+ * This is the drop-in boundary for RaulAstudillo06/BOPL's data-parallel hot path: the multi-output GP
+ * posterior and the uEI / uEI_affine acquisition over large candidate batches.  The reference is pure
+ * Python/NumPy with no FFI of its own; each entry point below names the reference function(s) it replaces
+ * (paths relative to /root/reference/bopl/, `GPy/`, `GPyOpt/` = aux_software/GPy, aux_software/GPyOpt).
+ * The ctypes binding a maintainer would add is shown in INTEGRATION.md and shipped in bopl_b200/_lib.py.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *  - every function returns 0 on success or a negative bopl_status; the message is available through
+ *    bopl_last_error(handle) (or bopl_last_error(NULL) when no handle exists yet).  No exceptions.
+ *  - all arrays are fp64, row-major (C order).  Pointers are DEVICE pointers unless the parameter name ends
+ *    in `_h` (host).  The caller owns every input/output buffer; the handle owns its copy of the model and
+ *    its scratch.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - calls on one handle are stream-ordered and not thread-safe; different handles are independent.
+ *  - there is no CPU fallback: without a CUDA device bopl_create fails.
+ */
+#ifndef BOPL_B200_H
+#define BOPL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bopl_handle bopl_handle;
+
+enum bopl_status {
+  BOPL_OK = 0,
+  BOPL_ERR_INVALID = -1,    /* bad argument */
+  BOPL_ERR_CUDA = -2,       /* CUDA runtime error (message has the cudaGetErrorString text) */
+  BOPL_ERR_STATE = -3,      /* call order: model not set, gradients requested without Winv, ... */
+  BOPL_ERR_UNSUPPORTED = -4 /* shape outside what the kernels are built for */
+};
+
+/* GPy kernel `.name` -> tag.  GPy/kern/src/stationary.py:516 (Mat52), :427 (Mat32), :581 (ExpQuad), rbf.py:22 (rbf). */
+enum bopl_kernel_kind { BOPL_KERN_MAT52 = 0, BOPL_KERN_RBF = 1, BOPL_KERN_MAT32 = 2, BOPL_KERN_EXPQUAD = 3 };
+
+/* Utility callables of the named experiment configs (Python callables in the reference, a tag here):
+ * linear      U = theta . y                       experiments/test_dtlz1a_linear.py:51-55   (p = m)
+ * quadratic   U = -sum_j (y_j - theta_j)^2        experiments/test_dtlz2a_quad.py:51-57     (p = m)
+ * exponential U = (1/m) sum_j (1-exp(-theta y_j))/theta   experiments/test_vlmop3_exp.py:41-52 (p = 1) */
+enum bopl_utility_kind { BOPL_UTIL_LINEAR = 0, BOPL_UTIL_QUADRATIC = 1, BOPL_UTIL_EXPONENTIAL = 2 };
+
+/* bopl_posterior flags */
+#define BOPL_VAR_INCLUDE_NOISE 1 /* add the Gaussian likelihood variance: GPy/core/gp.py:416-417, likelihoods/gaussian.py:110-111 */
+#define BOPL_VAR_CLIP 2          /* clip at 1e-10: GPyOpt/models/gpmodel.py:214 */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int bopl_create(bopl_handle** out, int device);
+void bopl_destroy(bopl_handle* h);
+const char* bopl_last_error(const bopl_handle* h);
+/* SM count of the handle's device and the library's build tag ("sm_100a ..."). */
+int bopl_device_sms(const bopl_handle* h);
+const char* bopl_build_info(void);
+
+/* ---- model state ----------------------------------------------------------------------------------------
+ * Replaces the cached state of m x H `GPy.models.GPRegression` instances that the reference keeps as live
+ * Python objects: GPyOpt/models/gpmodel.py:123-140 (model_instances[h]) per attribute of
+ * models/multi_outputGP.py:46-54; the arrays are those of GPy/inference/latent_function_inference/
+ * exact_gaussian_inference.py:46-65 and posterior.py:171-191.  All HOST pointers; copied in (synchronous).
+ *   kern_kind_h [m*H]      bopl_kernel_kind per (attribute j, hyper-sample h), index j*H + h (same for all below)
+ *   X_h         [n*d]      training inputs (shared by the attributes)
+ *   ell_h       [m*H*d]    ARD lengthscales (repeat the scalar d times for a non-ARD kernel)
+ *   var_h, noise_h, ymean_h [m*H]   kernel variance, Gaussian noise variance, normaliser mean
+ *   L_h         [m*H*n*n]  lower Cholesky factor of K + (noise+1e-8) I, row-major (upper part ignored)
+ *   alpha_h     [m*H*n]    woodbury vector
+ *   Winv_h      [m*H*n*n]  woodbury inverse (symmetric) or NULL when gradients are never requested          */
+int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
+                   const double* L_h, const double* alpha_h, const double* Winv_h);
+
+/* ---- kernel (1): cross-covariance ------------------------------------------------------------------------
+ * K(Xc, X) for attribute j under hyper-sample hsel -> K [N*n].  Replaces Stationary.K / _scaled_dist /
+ * K_of_r: GPy/kern/src/stationary.py:104-113,128-166,529-530,440-441,594-595; rbf.py:42-43.             */
+int bopl_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, double* K, void* stream);
+
+/* ---- kernels (1)+(2): posterior mean and variance -----------------------------------------------------------
+ * mean, var [m*N] (either may be NULL).  Replaces MultiOutputGP.posterior_mean / posterior_variance / predict /
+ * predict_noiseless: models/multi_outputGP.py:91-141 -> GPyOpt/models/gpmodel.py:170-223 -> GPy/core/gp.py:286-326,
+ * 380-435 -> posterior.py:268-320 (K(X,Xc), dtrtrs against the cached Cholesky factor, column square-sum).
+ * flags: BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP.                                                             */
+int bopl_posterior(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
+                   void* stream);
+
+/* Posterior mean only (no triangular solve), [m*N].  multi_outputGP.py:117-125. */
+int bopl_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, void* stream);
+
+/* Posterior mean at the evaluated (training) points for every hyper-sample: F [H*m*n].
+ * multi_outputGP.py:127-131. */
+int bopl_train_mean(bopl_handle* h, double* F, void* stream);
+
+/* Gradients of posterior mean and variance wrt the candidate: dmean, dvar [m*N*d] (either may be NULL).
+ * Replaces MultiOutputGP.posterior_mean_gradient / posterior_variance_gradient: multi_outputGP.py:225-246 ->
+ * GPy/core/gp.py:438-490 -> stationary.py:247-254,312-342,227-234 (+ C loop stationary_utils.c:1-14).
+ * Needs Winv for dvar. */
+int bopl_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, double* dmean, double* dvar,
+                        void* stream);
+
+/* ---- incumbents ---------------------------------------------------------------------------------------------
+ * best[h*Lt + l] = max_i U(F^h[:, i], theta_l) for h < H.  theta [Lt*p].
+ * uEI.py:77,112,153; uEI_affine.py:118-125 (linear). */
+int bopl_incumbent(bopl_handle* h, int util_kind, const double* theta, int Lt, int p, double* best, void* stream);
+
+/* ---- kernel (3): fused MC expected-utility improvement --------------------------------------------------------
+ * acq[i] (+)= scale * sum_l wts[l] * sum_k max(U(mean[:,i] + sqrt(var[:,i]) * Z[k,:], theta_l) - best[l], 0)
+ * given mean, var [m*N].  Z [nw*m], theta [Lt*p], wts [Lt], best [Lt].  accumulate != 0 adds into acq.
+ * Replaces the h-loop body of uEI._marginal_acq / _parallel_acq_helper + the theta aggregation of _compute_acq:
+ * sampling_policies/acquisition_functions/uEI.py:72-81,105-115,56-59.                                           */
+int bopl_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, const double* Z, int nw,
+                int util_kind, const double* theta, int Lt, int p, const double* wts, const double* best,
+                double scale, int accumulate, double* acq, void* stream);
+
+/* Full batch acquisition value: for hh < nH: posterior under hyper-sample hh, then the MC kernel with
+ * best + hh*Lt, scale 1/(nH*nw).  acq [N].  Replaces uEI._compute_acq: uEI.py:40-62 (batch and N==1 paths; the
+ * caller chooses per-h or stale incumbents by what it puts in `best` [nH*Lt]).                                   */
+int bopl_uei(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+             const double* theta, int Lt, int p, const double* wts, const double* best, int nH, double* acq,
+             void* stream);
+
+/* Value and analytic gradient: acq [N], dacq [N*d].  Replaces uEI._compute_acq_withGradients /
+ * _marginal_acq_with_gradient: uEI.py:119-168 (strict `>` mask, b = dmu + 0.5 W/sigma * dvar). Needs Winv. */
+int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+                  const double* theta, int Lt, int p, const double* wts, const double* best, int nH,
+                  double* acq, double* dacq, void* stream);
+
+/* Closed-form EI of a linear utility: acq [N], dacq [N*d] or NULL.  theta [Lt*m], best [nH*Lt].
+ * value path (dacq == NULL): uEI_affine._marginal_acq + _get_quantiles, uEI_affine.py:73-89,127-142 (sigma floor 1e-10);
+ * gradient path: uEI_affine._marginal_acq_with_gradient, uEI_affine.py:91-116 (no floor).                       */
+int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
+                    const double* best, int nH, double* acq, double* dacq, void* stream);
+
+/* ---- anchor selection ---------------------------------------------------------------------------------------
+ * The k largest acq values of this shard, ties -> lowest index; idx are GLOBAL indices (local + index_offset).
+ * val [k], idx [k] (device).  Replaces np.argsort(-acq)[:k]: GPyOpt/optimization/anchor_points_generator.py:58-62. */
+int bopl_topk(bopl_handle* h, const double* acq, int N, int k, long long index_offset, double* val,
+              long long* idx, void* stream);
+
+/* ---- host-buffer convenience (the reference-facing call: NumPy arrays in, NumPy arrays out) ------------------
+ * Same as bopl_uei (+ bopl_topk when k > 0) with HOST buffers; host<->device copies happen inside, chunked and
+ * overlapped with compute on the handle's own streams; returns after the results are on the host.
+ * acq_h [N] may be NULL when only the top-k is wanted.  topk_* may be NULL when k == 0.                          */
+int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, int nw, int util_kind,
+                  const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
+                  double* acq_h, int k, long long index_offset, double* topk_val_h, long long* topk_idx_h);
+
+/* Number of kernel launches issued through this handle since creation (bench.py reports the delta). */
+long long bopl_launch_count(const bopl_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOPL_B200_H */
