@@ -1,0 +1,490 @@
+// api.cu — the C-ABI of libbopl_b200.so (include/bopl_b200.h): handle lifetime, model upload and the entry points
+// that sequence the kernels.  Plain pointers and sizes only; every entry returns a bopl_status.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace bopl {
+
+thread_local std::string g_err;
+
+int fail(bopl_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+
+int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return BOPL_OK;
+  if (*p) {
+    BOPL_CUDA(h, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+  }
+  BOPL_CUDA(h, cudaMalloc(p, bytes));
+  *cap = bytes;
+  return BOPL_OK;
+}
+
+namespace {
+
+void free_model(bopl_handle* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->gp_host.clear();
+  h->gp_dev = nullptr;
+  h->X_dev = nullptr;
+  h->has_model = false;
+  h->has_winv = false;
+  h->F_valid = false;
+}
+
+template <typename T>
+int dev_upload(bopl_handle* h, const T* src, size_t count, T** out) {
+  void* p = nullptr;
+  BOPL_CUDA(h, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  h->owned.push_back(p);
+  if (count) BOPL_CUDA(h, cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (T*)p;
+  return BOPL_OK;
+}
+
+// Inverse of a lower-triangular B x B block (row-major, leading dimension ld) in extended precision.
+// Returns false on a non-positive diagonal.
+bool invert_lower_block(const double* D, int ld, int B, double* out) {
+  std::vector<long double> x((size_t)B * B, 0.0L);
+  for (int c = 0; c < B; ++c) {
+    long double dcc = D[(size_t)c * ld + c];
+    if (!(dcc > 0.0L)) return false;
+    x[(size_t)c * B + c] = 1.0L / dcc;
+    for (int r = c + 1; r < B; ++r) {
+      long double s = 0.0L;
+      for (int k = c; k < r; ++k) s += (long double)D[(size_t)r * ld + k] * x[(size_t)k * B + c];
+      long double drr = D[(size_t)r * ld + r];
+      if (!(drr > 0.0L)) return false;
+      x[(size_t)r * B + c] = -s / drr;
+    }
+  }
+  for (size_t i = 0; i < (size_t)B * B; ++i) out[i] = (double)x[i];
+  return true;
+}
+
+#define BOPL_CHECK_HANDLE(h)                                             \
+  do {                                                                   \
+    if (!(h)) return bopl::fail(nullptr, BOPL_ERR_INVALID, "null handle"); \
+    BOPL_CUDA((h), cudaSetDevice((h)->device));                           \
+  } while (0)
+
+#define BOPL_NEED_MODEL(h)                                                                        \
+  do {                                                                                            \
+    if (!(h)->has_model) return bopl::fail((h), BOPL_ERR_STATE, "bopl_set_model has not been called"); \
+  } while (0)
+
+int check_utility(bopl_handle* h, int util_kind, int Lt, int p) {
+  if (Lt <= 0) return fail(h, BOPL_ERR_INVALID, "Lt must be positive");
+  if (util_kind == BOPL_UTIL_LINEAR || util_kind == BOPL_UTIL_QUADRATIC) {
+    if (p != h->m) return fail(h, BOPL_ERR_INVALID, "linear/quadratic utility needs p == m parameters per sample");
+  } else if (util_kind == BOPL_UTIL_EXPONENTIAL) {
+    if (p != 1) return fail(h, BOPL_ERR_INVALID, "exponential utility needs p == 1");
+  } else {
+    return fail(h, BOPL_ERR_INVALID, "unknown utility kind (no CPU fallback for arbitrary callables)");
+  }
+  return BOPL_OK;
+}
+
+int ensure_mv(bopl_handle* h, size_t count) {
+  int rc = ensure_bytes(h, (void**)&h->mean_s, &h->mean_bytes, count * sizeof(double));
+  if (rc) return rc;
+  return ensure_bytes(h, (void**)&h->var_s, &h->var_bytes, count * sizeof(double));
+}
+
+int ensure_grad(bopl_handle* h, size_t count) {
+  int rc = ensure_bytes(h, (void**)&h->dmean_s, &h->dmean_bytes, count * sizeof(double));
+  if (rc) return rc;
+  return ensure_bytes(h, (void**)&h->dvar_s, &h->dvar_bytes, count * sizeof(double));
+}
+
+int train_mean(bopl_handle* h, double* F, cudaStream_t st) {
+  for (int hh = 0; hh < h->H; ++hh) {
+    int rc = launch_posterior_mean_strided(h, h->X_dev, h->n, hh, F + (size_t)hh * h->m * h->n, h->n, st);
+    if (rc) return rc;
+  }
+  return BOPL_OK;
+}
+
+// acq [N] on the device, all inputs on the device.
+int uei_device(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind, const double* theta,
+               int Lt, int p, const double* wts, const double* best, int nH, double* acq, cudaStream_t st) {
+  int rc = ensure_mv(h, (size_t)h->m * N);
+  if (rc) return rc;
+  const double scale = 1.0 / ((double)nH * (double)nw);
+  for (int hh = 0; hh < nH; ++hh) {
+    rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st);
+    if (rc) return rc;
+    rc = launch_uei_mc(h, h->mean_s, h->var_s, N, Z, nw, util_kind, theta, Lt, p, wts, best + (size_t)hh * Lt, scale,
+                       hh > 0, acq, st);
+    if (rc) return rc;
+  }
+  return BOPL_OK;
+}
+
+}  // namespace
+
+}  // namespace bopl
+
+using namespace bopl;
+
+extern "C" {
+
+int bopl_create(bopl_handle** out, int device) {
+  if (!out) return fail(nullptr, BOPL_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, BOPL_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, BOPL_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, BOPL_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, BOPL_ERR_UNSUPPORTED,
+                std::string("libbopl_b200 is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  bopl_handle* h = new bopl_handle();
+  h->device = device;
+  h->sms = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, BOPL_ERR_CUDA, cudaGetErrorString(e));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+  }
+  *out = h;
+  return BOPL_OK;
+}
+
+void bopl_destroy(bopl_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_model(h);
+  void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  delete h;
+}
+
+const char* bopl_last_error(const bopl_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int bopl_device_sms(const bopl_handle* h) { return h ? h->sms : 0; }
+
+const char* bopl_build_info(void) { return "libbopl_b200 sm_100a (compute_100a) fp64 DMMA.8x8x4 " __DATE__; }
+
+long long bopl_launch_count(const bopl_handle* h) { return h ? h->launches : 0; }
+
+int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
+                   const double* L_h, const double* alpha_h, const double* Winv_h) {
+  BOPL_CHECK_HANDLE(h);
+  if (n <= 0 || d <= 0 || m <= 0 || H <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, m, H must be positive");
+  if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
+  if (m > MAX_M) return fail(h, BOPL_ERR_UNSUPPORTED, "m > 16 attributes");
+  if (!kern_kind_h || !X_h || !ell_h || !var_h || !noise_h || !ymean_h || !L_h || !alpha_h)
+    return fail(h, BOPL_ERR_INVALID, "null model array");
+  for (int i = 0; i < m * H; ++i) {
+    if (kern_kind_h[i] < BOPL_KERN_MAT52 || kern_kind_h[i] > BOPL_KERN_EXPQUAD) return fail(h, BOPL_ERR_INVALID, "unknown kernel kind");
+    if (!(var_h[i] > 0.0) || !(noise_h[i] >= 0.0)) return fail(h, BOPL_ERR_INVALID, "kernel variance must be > 0 and noise >= 0");
+    for (int q = 0; q < d; ++q)
+      if (!(ell_h[(size_t)i * d + q] > 0.0)) return fail(h, BOPL_ERR_INVALID, "lengthscales must be > 0");
+  }
+  BOPL_CUDA(h, cudaDeviceSynchronize());
+  free_model(h);
+  h->n = n;
+  h->d = d;
+  h->m = m;
+  h->H = H;
+  h->n_pad = ((n + TRSM_BM - 1) / TRSM_BM) * TRSM_BM;
+  h->pad = h->n_pad - n;
+  const int n_pad = h->n_pad, pad = h->pad, nblk = n_pad / TRSM_BM;
+  int rc;
+  if ((rc = dev_upload(h, X_h, (size_t)n * d, &h->X_dev))) return rc;
+
+  std::vector<double> Lp((size_t)n_pad * n_pad);
+  std::vector<double> Dinv((size_t)nblk * TRSM_BM * TRSM_BM);
+  std::vector<double> Xs((size_t)n_pad * d), al((size_t)n_pad);
+  h->gp_host.resize((size_t)m * H);
+  for (int g = 0; g < m * H; ++g) {
+    const double* L = L_h + (size_t)g * n * n;
+    // front-padded factor: identity on the pad x pad leading block, the real factor below/right of it
+    std::fill(Lp.begin(), Lp.end(), 0.0);
+    for (int i = 0; i < pad; ++i) Lp[(size_t)i * n_pad + i] = 1.0;
+    for (int i = 0; i < n; ++i) {
+      double* row = Lp.data() + (size_t)(pad + i) * n_pad + pad;
+      const double* src = L + (size_t)i * n;
+      for (int k = 0; k <= i; ++k) row[k] = src[k];
+    }
+    for (int b = 0; b < nblk; ++b)
+      if (!invert_lower_block(Lp.data() + (size_t)b * TRSM_BM * n_pad + (size_t)b * TRSM_BM, n_pad, TRSM_BM,
+                              Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM)) {
+        free_model(h);
+        return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
+      }
+    // negate the off-diagonal blocks so that the kernel's update is a pure accumulate: acc += (-L) V
+    for (int i = 0; i < n_pad; ++i) {
+      const int bi = i / TRSM_BM;
+      double* row = Lp.data() + (size_t)i * n_pad;
+      for (int k = 0; k < bi * TRSM_BM; ++k) row[k] = -row[k];
+    }
+    std::fill(Xs.begin(), Xs.end(), 0.0);
+    std::fill(al.begin(), al.end(), 0.0);
+    const double* ell = ell_h + (size_t)g * d;
+    for (int i = 0; i < n; ++i) {
+      for (int q = 0; q < d; ++q) Xs[(size_t)(pad + i) * d + q] = X_h[(size_t)i * d + q] / ell[q];   // stationary.py:161-162
+      al[pad + i] = alpha_h[(size_t)g * n + i];
+    }
+    GpDev gp{};
+    double *pL, *pD, *pX, *pa, *pe, *pW = nullptr;
+    if ((rc = dev_upload(h, Lp.data(), Lp.size(), &pL)) || (rc = dev_upload(h, Dinv.data(), Dinv.size(), &pD)) ||
+        (rc = dev_upload(h, Xs.data(), Xs.size(), &pX)) || (rc = dev_upload(h, al.data(), al.size(), &pa)) ||
+        (rc = dev_upload(h, ell, (size_t)d, &pe))) {
+      free_model(h);
+      return rc;
+    }
+    if (Winv_h && (rc = dev_upload(h, Winv_h + (size_t)g * n * n, (size_t)n * n, &pW))) {
+      free_model(h);
+      return rc;
+    }
+    gp.Lneg = pL;
+    gp.Dinv = pD;
+    gp.Xs = pX;
+    gp.alpha = pa;
+    gp.ell = pe;
+    gp.Winv = pW;
+    gp.variance = var_h[g];
+    gp.noise = noise_h[g];
+    gp.ymean = ymean_h[g];
+    gp.kind = kern_kind_h[g];
+    h->gp_host[g] = gp;
+  }
+  GpDev* gd;
+  if ((rc = dev_upload(h, h->gp_host.data(), h->gp_host.size(), &gd))) {
+    free_model(h);
+    return rc;
+  }
+  h->gp_dev = gd;
+  h->has_winv = Winv_h != nullptr;
+  h->has_model = true;
+  h->F_valid = false;
+  return BOPL_OK;
+}
+
+int bopl_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, double* K, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || hsel < 0 || hsel >= h->H || j < 0 || j >= h->m) return fail(h, BOPL_ERR_INVALID, "bad N / hsel / j");
+  if (N && (!Xc || !K)) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return launch_cross_cov(h, Xc, N, hsel, j, K, (cudaStream_t)stream);
+}
+
+int bopl_posterior(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
+                   void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
+  if (N && !Xc) return fail(h, BOPL_ERR_INVALID, "null candidates");
+  if (!var) return mean ? launch_posterior_mean(h, Xc, N, hsel, mean, (cudaStream_t)stream) : BOPL_OK;
+  return launch_posterior_trsm(h, Xc, N, hsel, mean, var, flags, (cudaStream_t)stream);
+}
+
+int bopl_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
+  if (N && (!Xc || !mean)) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return launch_posterior_mean(h, Xc, N, hsel, mean, (cudaStream_t)stream);
+}
+
+int bopl_train_mean(bopl_handle* h, double* F, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (!F) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return train_mean(h, F, (cudaStream_t)stream);
+}
+
+int bopl_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, double* dmean, double* dvar,
+                        void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
+  if (N && !Xc) return fail(h, BOPL_ERR_INVALID, "null candidates");
+  if (dvar && !h->has_winv) return fail(h, BOPL_ERR_STATE, "variance gradient needs Winv (bopl_set_model was given NULL)");
+  return launch_posterior_grad(h, Xc, N, hsel, dmean, dvar, (cudaStream_t)stream);
+}
+
+int bopl_incumbent(bopl_handle* h, int util_kind, const double* theta, int Lt, int p, double* best, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (!theta || !best) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need = (size_t)h->H * h->m * h->n * sizeof(double);
+  if (!h->F_s || h->F_bytes < need) {
+    rc = ensure_bytes(h, (void**)&h->F_s, &h->F_bytes, need);
+    if (rc) return rc;
+    h->F_valid = false;
+  }
+  if (!h->F_valid) {
+    rc = train_mean(h, h->F_s, st);
+    if (rc) return rc;
+    h->F_valid = true;   // later calls on other streams: the caller orders streams (calls on a handle are stream-ordered)
+  }
+  return launch_incumbent(h, h->F_s, util_kind, theta, Lt, p, best, st);
+}
+
+int bopl_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, const double* Z, int nw,
+                int util_kind, const double* theta, int Lt, int p, const double* wts, const double* best,
+                double scale, int accumulate, double* acq, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (N < 0 || nw <= 0) return fail(h, BOPL_ERR_INVALID, "bad N / nw");
+  if (N && (!mean || !var || !Z || !theta || !wts || !best || !acq)) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return launch_uei_mc(h, mean, var, N, Z, nw, util_kind, theta, Lt, p, wts, best, scale, accumulate, acq,
+                       (cudaStream_t)stream);
+}
+
+int bopl_uei(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+             const double* theta, int Lt, int p, const double* wts, const double* best, int nH, double* acq,
+             void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
+  if (N == 0) return BOPL_OK;
+  if (!Xc || !Z || !theta || !wts || !best || !acq) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return uei_device(h, Xc, N, Z, nw, util_kind, theta, Lt, p, wts, best, nH, acq, (cudaStream_t)stream);
+}
+
+int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+                  const double* theta, int Lt, int p, const double* wts, const double* best, int nH,
+                  double* acq, double* dacq, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
+  if (N == 0) return BOPL_OK;
+  if (!Xc || !Z || !theta || !wts || !best || !acq || !dacq) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (!h->has_winv) return fail(h, BOPL_ERR_STATE, "gradients need Winv (bopl_set_model was given NULL)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_mv(h, (size_t)h->m * N)) || (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
+  const double scale = 1.0 / ((double)nH * (double)nw);
+  for (int hh = 0; hh < nH; ++hh) {
+    if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
+    if ((rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
+    if ((rc = launch_uei_mc_grad(h, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, N, Z, nw, util_kind, theta, Lt, p, wts,
+                                 best + (size_t)hh * Lt, scale, hh > 0, acq, dacq, st)))
+      return rc;
+  }
+  return BOPL_OK;
+}
+
+int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
+                    const double* best, int nH, double* acq, double* dacq, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || Lt <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / Lt / nH");
+  if (N == 0) return BOPL_OK;
+  if (!Xc || !theta || !wts || !best || !acq) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (dacq && !h->has_winv) return fail(h, BOPL_ERR_STATE, "gradients need Winv (bopl_set_model was given NULL)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
+  if (dacq && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
+  const double scale = 1.0 / (double)nH;
+  for (int hh = 0; hh < nH; ++hh) {
+    if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
+    if (dacq && (rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
+    if ((rc = launch_uei_affine(h, h->mean_s, h->var_s, dacq ? h->dmean_s : nullptr, dacq ? h->dvar_s : nullptr, N, theta,
+                                Lt, wts, best + (size_t)hh * Lt, scale, hh > 0, acq, dacq, st)))
+      return rc;
+  }
+  return BOPL_OK;
+}
+
+int bopl_topk(bopl_handle* h, const double* acq, int N, int k, long long index_offset, double* val,
+              long long* idx, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  if (N < 0 || k < 0) return fail(h, BOPL_ERR_INVALID, "bad N / k");
+  if (k == 0) return BOPL_OK;
+  if (!acq || !val || !idx) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  return launch_topk(h, acq, N, k, index_offset, val, idx, (cudaStream_t)stream);
+}
+
+int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, int nw, int util_kind,
+                  const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
+                  double* acq_h, int k, long long index_offset, double* topk_val_h, long long* topk_idx_h) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H || k < 0) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH / k");
+  if (N == 0) return k ? fail(h, BOPL_ERR_INVALID, "topk of an empty batch") : BOPL_OK;
+  if (!Xc_h || !Z_h || !theta_h || !wts_h || !best_h) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (k && (!topk_val_h || !topk_idx_h)) return fail(h, BOPL_ERR_INVALID, "null top-k buffer");
+  if (k > N) return fail(h, BOPL_ERR_INVALID, "topk: fewer candidates than k");
+  const int d = h->d;
+  // chunk = a whole number of persistent waves of the posterior kernel (sms candidate tiles of 128) so no chunk has a tail
+  const int chunk = std::min(N, h->sms * TRSM_BC * 8);
+  const size_t small_cnt = (size_t)nw * h->m + (size_t)Lt * p + Lt + (size_t)nH * Lt + k + k;
+  if ((rc = ensure_bytes(h, (void**)&h->hx_dev, &h->hx_cap, (size_t)2 * chunk * d * sizeof(double)))) return rc;
+  if ((rc = ensure_bytes(h, (void**)&h->hacq_dev, &h->hacq_cap, (size_t)N * sizeof(double)))) return rc;
+  if ((rc = ensure_bytes(h, (void**)&h->hsmall_dev, &h->hsmall_cap, small_cnt * sizeof(double)))) return rc;
+  double* Zd = h->hsmall_dev;
+  double* thd = Zd + (size_t)nw * h->m;
+  double* wd = thd + (size_t)Lt * p;
+  double* bd = wd + Lt;
+  double* tkv = bd + (size_t)nH * Lt;
+  long long* tki = (long long*)(tkv + k);
+  cudaStream_t sc = h->s_compute, sy = h->s_copy;
+  BOPL_CUDA(h, cudaMemcpyAsync(Zd, Z_h, (size_t)nw * h->m * sizeof(double), cudaMemcpyHostToDevice, sc));
+  BOPL_CUDA(h, cudaMemcpyAsync(thd, theta_h, (size_t)Lt * p * sizeof(double), cudaMemcpyHostToDevice, sc));
+  BOPL_CUDA(h, cudaMemcpyAsync(wd, wts_h, (size_t)Lt * sizeof(double), cudaMemcpyHostToDevice, sc));
+  BOPL_CUDA(h, cudaMemcpyAsync(bd, best_h, (size_t)nH * Lt * sizeof(double), cudaMemcpyHostToDevice, sc));
+  int ci = 0;
+  for (int s = 0; s < N; s += chunk, ++ci) {
+    const int nc = std::min(chunk, N - s), buf = ci & 1;
+    double* xb = h->hx_dev + (size_t)buf * chunk * d;
+    if (ci >= 2) BOPL_CUDA(h, cudaStreamWaitEvent(sy, h->ev_done[buf], 0));
+    BOPL_CUDA(h, cudaMemcpyAsync(xb, Xc_h + (size_t)s * d, (size_t)nc * d * sizeof(double), cudaMemcpyHostToDevice, sy));
+    BOPL_CUDA(h, cudaEventRecord(h->ev_in[buf], sy));
+    BOPL_CUDA(h, cudaStreamWaitEvent(sc, h->ev_in[buf], 0));
+    if ((rc = uei_device(h, xb, nc, Zd, nw, util_kind, thd, Lt, p, wd, bd, nH, h->hacq_dev + s, sc))) return rc;
+    BOPL_CUDA(h, cudaEventRecord(h->ev_done[buf], sc));
+  }
+  if (acq_h) BOPL_CUDA(h, cudaMemcpyAsync(acq_h, h->hacq_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, sc));
+  if (k) {
+    if ((rc = launch_topk(h, h->hacq_dev, N, k, index_offset, tkv, tki, sc))) return rc;
+    BOPL_CUDA(h, cudaMemcpyAsync(topk_val_h, tkv, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, sc));
+    BOPL_CUDA(h, cudaMemcpyAsync(topk_idx_h, tki, (size_t)k * sizeof(long long), cudaMemcpyDeviceToHost, sc));
+  }
+  BOPL_CUDA(h, cudaStreamSynchronize(sc));
+  return BOPL_OK;
+}
+
+}  // extern "C"

@@ -48,14 +48,17 @@ struct bopl_handle {
   double* X_dev = nullptr;             // [n*d] unscaled training inputs
   // scratch
   double* trsm_scratch = nullptr; size_t trsm_scratch_bytes = 0;   // per-CTA V panels
-  double* mean_s = nullptr; double* var_s = nullptr; size_t mv_cap = 0;        // [m*N]
-  double* dmean_s = nullptr; double* dvar_s = nullptr; size_t grad_cap = 0;    // [m*N*d]
-  double* F_s = nullptr;                                                       // [H*m*n]
+  double* mean_s = nullptr; double* var_s = nullptr; size_t mean_bytes = 0, var_bytes = 0;        // [m*N]
+  double* dmean_s = nullptr; double* dvar_s = nullptr; size_t dmean_bytes = 0, dvar_bytes = 0;    // [m*N*d]
+  double* grad_scratch = nullptr; size_t grad_scratch_bytes = 0;               // K*, G, beta panels of the gradient path
+  double* acq_s = nullptr; size_t acq_cap = 0;                                 // [N] (host path / top-k only callers)
+  double* F_s = nullptr; size_t F_bytes = 0; bool F_valid = false;             // [H*m*n] posterior mean at the training points
   double* topk_val_s = nullptr; long long* topk_idx_s = nullptr; size_t topk_cap = 0;
   // host-path staging
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  double* hx_dev = nullptr; double* hacq_dev = nullptr; size_t host_cap = 0;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  double* hx_dev = nullptr; size_t hx_cap = 0;       // [2][chunk*d] candidate double buffer
+  double* hacq_dev = nullptr; size_t hacq_cap = 0;   // [N]
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
   size_t hsmall_cap = 0;
 };
@@ -87,6 +90,8 @@ int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes);
 int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                           cudaStream_t st);
 int launch_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, cudaStream_t st);
+int launch_posterior_mean_strided(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, long long out_stride,
+                                  cudaStream_t st);
 int launch_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, double* K, cudaStream_t st);
 int launch_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, double* dmean, double* dvar,
                           cudaStream_t st);

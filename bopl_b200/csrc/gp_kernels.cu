@@ -1,0 +1,330 @@
+// gp_kernels.cu — the non-TRSM GP kernels of the hot path:
+//   kstar_kernel            K(Xc, X) (and g = dK/dr / r) materialised, for bopl_cross_cov and the gradient path
+//   posterior_mean_kernel   mu = K(Xc, X) alpha + ymean without the triangular solve
+//   beta_gemv / beta_gemm   beta = -2 K(Xc, X) Winv                       (GPy/core/gp.py:474)
+//   grad_contract_kernel    d mu / dx and d var / dx                      (GPy/kern/src/stationary.py:312-322)
+// Reference: GPy/kern/src/stationary.py:104-171,227-254,312-342; GPy/core/gp.py:380-400,438-490;
+// inference/latent_function_inference/posterior.py:299-305.
+#include "common.cuh"
+
+namespace bopl {
+
+namespace {
+
+// --------------------------------------------------------------------------------------------- K*, G
+// Block: 16 candidates x all training rows.  Thread i-strided over training rows; writes are coalesced along n.
+constexpr int KS_TC = 16;
+constexpr int KS_NT = 256;
+
+template <bool WITH_G>
+__global__ void __launch_bounds__(KS_NT) kstar_kernel(GpDev gp, const double* __restrict__ Xc, int N, int d, int n, int pad,
+                                                       double* __restrict__ K, double* __restrict__ G) {
+  __shared__ double xc_s[KS_TC * MAX_D];
+  const int c0 = blockIdx.x * KS_TC;
+  for (int idx = threadIdx.x; idx < KS_TC * d; idx += KS_NT) {
+    int c = idx / d, q = idx - c * d;
+    int cc = min(c0 + c, N - 1);
+    xc_s[c * d + q] = Xc[(size_t)cc * d + q] / gp.ell[q];
+  }
+  __syncthreads();
+  const double* Xs = gp.Xs + (size_t)pad * d;
+  for (int i = blockIdx.y * KS_NT + threadIdx.x; i < n; i += gridDim.y * KS_NT) {
+    double xt[MAX_D];
+#pragma unroll
+    for (int q = 0; q < MAX_D; ++q)
+      if (q < d) xt[q] = Xs[(size_t)i * d + q];
+    for (int c = 0; c < KS_TC && c0 + c < N; ++c) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < MAX_D; ++q)
+        if (q < d) {
+          double df = xt[q] - xc_s[c * d + q];
+          r2 = fma(df, df, r2);
+        }
+      if (WITH_G) {
+        double k, g;
+        kern_value_grad(gp.kind, gp.variance, r2, k, g);
+        K[(size_t)(c0 + c) * n + i] = k;
+        G[(size_t)(c0 + c) * n + i] = g;
+      } else {
+        K[(size_t)(c0 + c) * n + i] = kern_value(gp.kind, gp.variance, r2);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- mean only
+// Block: 32 candidates; 256 threads = 32 candidates x 8 row groups.  Training rows are staged through shared
+// memory 128 at a time; the 8 row-group partial sums are combined in a fixed order (bit-stable run to run).
+constexpr int PM_TC = 32;
+constexpr int PM_RG = 8;
+constexpr int PM_ROWS = 128;
+
+struct MeanParams {
+  const GpDev* gps;
+  const double* Xc;
+  double* mean;
+  int H, hsel, m, N, d, n, pad;
+  long long out_stride;   // elements between attributes in `mean`
+};
+
+__global__ void __launch_bounds__(PM_TC* PM_RG) posterior_mean_kernel(MeanParams p) {
+  __shared__ double xc_s[MAX_D * PM_TC];
+  __shared__ double xt_s[PM_ROWS * MAX_D];
+  __shared__ double al_s[PM_ROWS];
+  __shared__ double red[PM_RG * PM_TC];
+  const int j = blockIdx.y;
+  const GpDev gp = p.gps[j * p.H + p.hsel];
+  const int d = p.d, n = p.n;
+  const int c = threadIdx.x & (PM_TC - 1), rg = threadIdx.x / PM_TC;
+  const int c0 = blockIdx.x * PM_TC;
+  for (int idx = threadIdx.x; idx < PM_TC * d; idx += PM_TC * PM_RG) {
+    int cc = idx / d, q = idx - cc * d;
+    int cg = min(c0 + cc, p.N - 1);
+    xc_s[q * PM_TC + cc] = p.Xc[(size_t)cg * d + q] / gp.ell[q];
+  }
+  const double* Xs = gp.Xs + (size_t)p.pad * d;
+  const double* al = gp.alpha + p.pad;
+  double acc = 0.0;
+  for (int r0 = 0; r0 < n; r0 += PM_ROWS) {
+    const int rows = min(PM_ROWS, n - r0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * d; idx += PM_TC * PM_RG) xt_s[idx] = Xs[(size_t)r0 * d + idx];
+    if (threadIdx.x < rows) al_s[threadIdx.x] = al[r0 + threadIdx.x];
+    __syncthreads();
+    for (int i = rg; i < rows; i += PM_RG) {
+      double r2 = 0.0;
+      for (int q = 0; q < d; ++q) {
+        double df = xt_s[i * d + q] - xc_s[q * PM_TC + c];
+        r2 = fma(df, df, r2);
+      }
+      acc = fma(kern_value(gp.kind, gp.variance, r2), al_s[i], acc);
+    }
+  }
+  red[rg * PM_TC + c] = acc;
+  __syncthreads();
+  if (rg == 0 && c0 + c < p.N) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < PM_RG; ++g) s += red[g * PM_TC + c];
+    p.mean[(size_t)j * p.out_stride + c0 + c] = s + gp.ymean;
+  }
+}
+
+// --------------------------------------------------------------------------------------------- beta = -2 K* Winv
+// Small batches (the L-BFGS inner loop calls with N = 1): one warp per training row i, Winv is symmetric so
+// beta[c][i] = -2 * dot(Winv[i, :], K*[c, :]) reads Winv rows coalesced.  Up to 4 candidates per pass.
+constexpr int GV_MAXC = 4;
+__global__ void __launch_bounds__(256) beta_gemv_kernel(const double* __restrict__ Winv, const double* __restrict__ K, int nc,
+                                                         int n, double* __restrict__ B) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double* w = Winv + (size_t)warp * n;
+  double acc[GV_MAXC];
+#pragma unroll
+  for (int c = 0; c < GV_MAXC; ++c) acc[c] = 0.0;
+  for (int k = lane; k < n; k += 32) {
+    double wv = w[k];
+#pragma unroll
+    for (int c = 0; c < GV_MAXC; ++c)
+      if (c < nc) acc[c] = fma(K[(size_t)c * n + k], wv, acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < GV_MAXC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && c < nc) B[(size_t)c * n + warp] = -2.0 * v;
+  }
+}
+
+// Larger batches: B[Nc x n] = -2 * K[Nc x n] * Winv[n x n] on the FP64 tensor pipe (DMMA.8x8x4).
+// CTA tile 64 (cands) x 64 (cols), k-step 16, 4 warps (2 x 2), warp tile 32 x 32 = 16 accumulators.
+constexpr int GM_BM = 64, GM_BN = 64, GM_BK = 16, GM_NT = 128;
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(GM_NT) beta_gemm_kernel(const double* __restrict__ Winv, const double* __restrict__ K, int nc,
+                                                           int n, double* __restrict__ B) {
+  // As[m][k] (k contiguous, +1 pad), Bs[k][nn] from Winv[k][col] (symmetric => also Winv[col][k]); store as Bs[nn][k].
+  __shared__ double As[GM_BM][GM_BK + 1];
+  __shared__ double Bs[GM_BN][GM_BK + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int r0 = blockIdx.y * GM_BM, col0 = blockIdx.x * GM_BN;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+  for (int k0 = 0; k0 < n; k0 += GM_BK) {
+    __syncthreads();
+    for (int idx = tid; idx < GM_BM * GM_BK; idx += GM_NT) {
+      int r = idx / GM_BK, k = idx - r * GM_BK;
+      As[r][k] = (r0 + r < nc && k0 + k < n) ? K[(size_t)(r0 + r) * n + k0 + k] : 0.0;
+      // Winv symmetric: element (k0+k, col0+r) == (col0+r, k0+k): read row (col0+r) contiguously along k
+      Bs[r][k] = (col0 + r < n && k0 + k < n) ? Winv[(size_t)(col0 + r) * n + k0 + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GM_BK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + 8 * i + g][kk + t];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) b[jj] = Bs[wn * 32 + 8 * jj + g][kk + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int r = r0 + wm * 32 + 8 * i + g, cidx = col0 + wn * 32 + 8 * jj + 2 * t + e;
+        if (r < nc && cidx < n) B[(size_t)r * n + cidx] = -2.0 * acc[i][jj][e];
+      }
+}
+
+// --------------------------------------------------------------------------------------------- gradient contraction
+// One block per (candidate, attribute):  out[q] = ( sum_i coef_i * G_i * (x_q - X_iq) ) / ell_q^2
+// with coef = alpha (mean gradient) and coef = beta (variance gradient).  Fixed reduction order.
+constexpr int GC_NT = 128;
+__global__ void __launch_bounds__(GC_NT) grad_contract_kernel(GpDev gp, const double* __restrict__ Xtrain, const double* __restrict__ Xc,
+                                                               int d, int n, int pad, const double* __restrict__ G,
+                                                               const double* __restrict__ Bt, double* __restrict__ dmean,
+                                                               double* __restrict__ dvar) {
+  __shared__ double red[2][GC_NT / 32][MAX_D];
+  const int c = blockIdx.x;
+  const double* g = G + (size_t)c * n;
+  const double* bt = Bt ? Bt + (size_t)c * n : nullptr;
+  const double* al = gp.alpha + pad;
+  double xq[MAX_D], am[MAX_D], av[MAX_D];
+#pragma unroll
+  for (int q = 0; q < MAX_D; ++q) {
+    xq[q] = (q < d) ? Xc[(size_t)c * d + q] : 0.0;
+    am[q] = 0.0;
+    av[q] = 0.0;
+  }
+  for (int i = threadIdx.x; i < n; i += GC_NT) {
+    double gi = g[i];
+    double cm = gi * al[i];            // tmp = invdist * dK_dr * dL_dK  (stationary.py:318)
+    double cv = bt ? gi * bt[i] : 0.0;
+#pragma unroll
+    for (int q = 0; q < MAX_D; ++q)
+      if (q < d) {
+        double df = xq[q] - Xtrain[(size_t)i * d + q];
+        am[q] = fma(cm, df, am[q]);
+        av[q] = fma(cv, df, av[q]);
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < MAX_D; ++q)
+    if (q < d) {
+      double a = am[q], v = av[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+      }
+      if (lane == 0) {
+        red[0][warp][q] = a;
+        red[1][warp][q] = v;
+      }
+    }
+  __syncthreads();
+  if (threadIdx.x < d) {
+    const int q = threadIdx.x;
+    double a = 0.0, v = 0.0;
+#pragma unroll
+    for (int w = 0; w < GC_NT / 32; ++w) {
+      a += red[0][w][q];
+      v += red[1][w][q];
+    }
+    double l2 = gp.ell[q] * gp.ell[q];
+    if (dmean) dmean[(size_t)c * d + q] = a / l2;
+    if (dvar) dvar[(size_t)c * d + q] = v / l2;
+  }
+}
+
+}  // namespace
+
+int launch_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, double* K, cudaStream_t st) {
+  if (N <= 0) return BOPL_OK;
+  const GpDev& gp = h->gp_host[j * h->H + hsel];
+  dim3 grid((N + KS_TC - 1) / KS_TC, std::max(1, std::min(8, (h->n + KS_NT - 1) / KS_NT)));
+  kstar_kernel<false><<<grid, KS_NT, 0, st>>>(gp, Xc, N, h->d, h->n, h->pad, K, nullptr);
+  BOPL_LAUNCH_CHECK(h, "kstar_kernel");
+  return BOPL_OK;
+}
+
+int launch_posterior_mean_strided(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, long long out_stride,
+                                  cudaStream_t st) {
+  if (N <= 0) return BOPL_OK;
+  MeanParams p;
+  p.gps = h->gp_dev;
+  p.Xc = Xc;
+  p.mean = mean;
+  p.H = h->H;
+  p.hsel = hsel;
+  p.m = h->m;
+  p.N = N;
+  p.d = h->d;
+  p.n = h->n;
+  p.pad = h->pad;
+  p.out_stride = out_stride;
+  dim3 grid((N + PM_TC - 1) / PM_TC, h->m);
+  posterior_mean_kernel<<<grid, PM_TC * PM_RG, 0, st>>>(p);
+  BOPL_LAUNCH_CHECK(h, "posterior_mean_kernel");
+  return BOPL_OK;
+}
+
+int launch_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, cudaStream_t st) {
+  return launch_posterior_mean_strided(h, Xc, N, hsel, mean, N, st);
+}
+
+// dmean, dvar [m*N*d].  Scratch: K, G, B  [chunk x n] each, reused per attribute.
+int launch_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, double* dmean, double* dvar,
+                          cudaStream_t st) {
+  if (N <= 0) return BOPL_OK;
+  const int n = h->n, d = h->d;
+  const int chunk = std::min(N, 2048);
+  size_t need = (size_t)3 * chunk * n * sizeof(double);
+  int rc = ensure_bytes(h, (void**)&h->grad_scratch, &h->grad_scratch_bytes, need);
+  if (rc) return rc;
+  double* Kb = h->grad_scratch;
+  double* Gb = Kb + (size_t)chunk * n;
+  double* Bb = Gb + (size_t)chunk * n;
+  for (int j = 0; j < h->m; ++j) {
+    const GpDev& gp = h->gp_host[j * h->H + hsel];
+    for (int s = 0; s < N; s += chunk) {
+      const int nc = std::min(chunk, N - s);
+      const double* xc = Xc + (size_t)s * d;
+      dim3 gridk((nc + KS_TC - 1) / KS_TC, std::max(1, std::min(8, (n + KS_NT - 1) / KS_NT)));
+      kstar_kernel<true><<<gridk, KS_NT, 0, st>>>(gp, xc, nc, d, n, h->pad, Kb, Gb);
+      BOPL_LAUNCH_CHECK(h, "kstar_kernel<G>");
+      if (dvar) {
+        if (nc <= GV_MAXC) {
+          beta_gemv_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
+          BOPL_LAUNCH_CHECK(h, "beta_gemv_kernel");
+        } else {
+          dim3 gg((n + GM_BN - 1) / GM_BN, (nc + GM_BM - 1) / GM_BM);
+          beta_gemm_kernel<<<gg, GM_NT, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
+          BOPL_LAUNCH_CHECK(h, "beta_gemm_kernel");
+        }
+      }
+      grad_contract_kernel<<<nc, GC_NT, 0, st>>>(gp, h->X_dev, xc, d, n, h->pad, Gb, dvar ? Bb : nullptr,
+                                                 dmean ? dmean + ((size_t)j * N + s) * d : nullptr,
+                                                 dvar ? dvar + ((size_t)j * N + s) * d : nullptr);
+      BOPL_LAUNCH_CHECK(h, "grad_contract_kernel");
+    }
+  }
+  return BOPL_OK;
+}
+
+}  // namespace bopl

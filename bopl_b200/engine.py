@@ -1,0 +1,227 @@
+"""Device engine: one `bopl_handle` (one GPU) behind a small Python object.
+
+PyTorch is used only to own device buffers and to name the stream; every computation goes through the C-ABI
+(`bopl_b200/_lib.py` -> libbopl_b200.so).  NumPy arrays in / NumPy arrays out for the reference-facing calls,
+torch CUDA tensors in / out for callers that keep data resident in HBM.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KERNEL_KINDS, UTILITY_KINDS, VAR_CLIP, VAR_INCLUDE_NOISE, BoplError, check
+
+
+class GPState(object):
+    """Flat fp64 arrays of m attributes x H hyper-samples of exact GPs — what `bopl_set_model` consumes.
+
+    kinds (m,H) of GPy kernel names; X (n,d); lengthscale (m,H,d); variance, noise, ymean (m,H);
+    L (m,H,n,n) lower Cholesky factors of K + (noise+1e-8) I, C order; alpha (m,H,n); Winv (m,H,n,n) or None.
+    Field map from the reference's live objects: SURVEY.md §7.1-10."""
+
+    def __init__(self, kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv=None):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.n, self.d = self.X.shape
+        self.variance = np.ascontiguousarray(variance, dtype=np.float64)
+        self.m, self.H = self.variance.shape
+        self.kinds = np.asarray(kinds).reshape(self.m, self.H)
+        self.lengthscale = np.ascontiguousarray(lengthscale, dtype=np.float64).reshape(self.m, self.H, self.d)
+        self.noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(self.m, self.H)
+        self.ymean = np.ascontiguousarray(ymean, dtype=np.float64).reshape(self.m, self.H)
+        self.L = np.ascontiguousarray(L, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
+        self.alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(self.m, self.H, self.n)
+        self.Winv = None if Winv is None else \
+            np.ascontiguousarray(Winv, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine(object):
+    """One GPU.  Methods taking `*_dev` arguments expect torch CUDA fp64 tensors on this engine's device."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise BoplError(-2, "no CUDA device: bopl_b200 has no CPU fallback")
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = ctypes.c_void_p()
+        check(self.lib.bopl_create(ctypes.byref(h), self.device_index))
+        self.h = h
+        self.state = None
+        self.sms = self.lib.bopl_device_sms(self.h)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.bopl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        check(rc, self.h)
+
+    def to_dev(self, a):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+
+    def empty(self, *shape):
+        torch = _torch()
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.bopl_launch_count(self.h))
+
+    # ------------------------------------------------------------------ model
+    def set_model(self, state):
+        kinds = np.ascontiguousarray([[KERNEL_KINDS[str(k)] for k in row] for row in state.kinds], dtype=np.int32)
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self._check(self.lib.bopl_set_model(
+            self.h, state.n, state.d, state.m, state.H, p(kinds), p(state.X), p(state.lengthscale), p(state.variance),
+            p(state.noise), p(state.ymean), p(state.L), p(state.alpha),
+            p(state.Winv) if state.Winv is not None else None))
+        self.state = state
+        self.n, self.d, self.m, self.H = state.n, state.d, state.m, state.H
+
+    # ------------------------------------------------------------------ posterior (device tensors)
+    def cross_cov_dev(self, Xc, hsel, j):
+        N = Xc.shape[0]
+        K = self.empty(N, self.n)
+        self._check(self.lib.bopl_cross_cov(self.h, Xc.data_ptr(), N, hsel, j, K.data_ptr(), self._stream()))
+        return K
+
+    def posterior_dev(self, Xc, hsel, include_noise=True, clip=True, want_mean=True, want_var=True):
+        N = Xc.shape[0]
+        mean = self.empty(self.m, N) if want_mean else None
+        var = self.empty(self.m, N) if want_var else None
+        flags = (VAR_INCLUDE_NOISE if include_noise else 0) | (VAR_CLIP if clip else 0)
+        self._check(self.lib.bopl_posterior(self.h, Xc.data_ptr(), N, hsel, mean.data_ptr() if want_mean else None,
+                                            var.data_ptr() if want_var else None, flags, self._stream()))
+        return mean, var
+
+    def posterior_mean_dev(self, Xc, hsel):
+        N = Xc.shape[0]
+        mean = self.empty(self.m, N)
+        self._check(self.lib.bopl_posterior_mean(self.h, Xc.data_ptr(), N, hsel, mean.data_ptr(), self._stream()))
+        return mean
+
+    def train_mean_dev(self):
+        F = self.empty(self.H, self.m, self.n)
+        self._check(self.lib.bopl_train_mean(self.h, F.data_ptr(), self._stream()))
+        return F
+
+    def posterior_grad_dev(self, Xc, hsel, want_mean=True, want_var=True):
+        N = Xc.shape[0]
+        dmean = self.empty(self.m, N, self.d) if want_mean else None
+        dvar = self.empty(self.m, N, self.d) if want_var else None
+        self._check(self.lib.bopl_posterior_grad(self.h, Xc.data_ptr(), N, hsel,
+                                                 dmean.data_ptr() if want_mean else None,
+                                                 dvar.data_ptr() if want_var else None, self._stream()))
+        return dmean, dvar
+
+    # ------------------------------------------------------------------ acquisition (device tensors)
+    def incumbent_dev(self, kind, theta):
+        Lt, p = theta.shape
+        best = self.empty(self.H, Lt)
+        self._check(self.lib.bopl_incumbent(self.h, UTILITY_KINDS[kind], theta.data_ptr(), Lt, p, best.data_ptr(),
+                                            self._stream()))
+        return best
+
+    def uei_mc_dev(self, mean, var, Z, kind, theta, wts, best, scale, acq=None, accumulate=False):
+        N = mean.shape[1]
+        Lt, p = theta.shape
+        if acq is None:
+            acq = self.empty(N)
+        self._check(self.lib.bopl_uei_mc(self.h, mean.data_ptr(), var.data_ptr(), N, Z.data_ptr(), Z.shape[0],
+                                         UTILITY_KINDS[kind], theta.data_ptr(), Lt, p, wts.data_ptr(), best.data_ptr(),
+                                         float(scale), int(bool(accumulate)), acq.data_ptr(), self._stream()))
+        return acq
+
+    def uei_dev(self, Xc, Z, kind, theta, wts, best, nH, acq=None):
+        N = Xc.shape[0]
+        Lt, p = theta.shape
+        if acq is None:
+            acq = self.empty(N)
+        self._check(self.lib.bopl_uei(self.h, Xc.data_ptr(), N, Z.data_ptr(), Z.shape[0], UTILITY_KINDS[kind],
+                                      theta.data_ptr(), Lt, p, wts.data_ptr(), best.data_ptr(), nH, acq.data_ptr(),
+                                      self._stream()))
+        return acq
+
+    def uei_grad_dev(self, Xc, Z, kind, theta, wts, best, nH):
+        N = Xc.shape[0]
+        Lt, p = theta.shape
+        acq = self.empty(N)
+        dacq = self.empty(N, self.d)
+        self._check(self.lib.bopl_uei_grad(self.h, Xc.data_ptr(), N, Z.data_ptr(), Z.shape[0], UTILITY_KINDS[kind],
+                                           theta.data_ptr(), Lt, p, wts.data_ptr(), best.data_ptr(), nH,
+                                           acq.data_ptr(), dacq.data_ptr(), self._stream()))
+        return acq, dacq
+
+    def uei_affine_dev(self, Xc, theta, wts, best, nH, with_grad=False):
+        N = Xc.shape[0]
+        Lt = theta.shape[0]
+        acq = self.empty(N)
+        dacq = self.empty(N, self.d) if with_grad else None
+        self._check(self.lib.bopl_uei_affine(self.h, Xc.data_ptr(), N, theta.data_ptr(), Lt, wts.data_ptr(),
+                                             best.data_ptr(), nH, acq.data_ptr(),
+                                             dacq.data_ptr() if with_grad else None, self._stream()))
+        return acq, dacq
+
+    def topk_dev(self, acq, k, index_offset=0):
+        torch = _torch()
+        N = acq.shape[0]
+        val = self.empty(k)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        self._check(self.lib.bopl_topk(self.h, acq.data_ptr(), N, k, int(index_offset), val.data_ptr(), idx.data_ptr(),
+                                       self._stream()))
+        return val, idx
+
+    # ------------------------------------------------------------------ host-buffer path (the reference-facing call)
+    def uei_host(self, Xc, Z, kind, theta, wts, best, nH, k=0, index_offset=0, want_acq=True, out=None):
+        """NumPy in / NumPy out through `bopl_uei_host` (chunked H2D overlapped with compute inside the library).
+        Xc may be a pinned torch CPU tensor or a NumPy array; it must be C-contiguous fp64."""
+        torch = _torch()
+
+        def hp(a):
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.dtype == torch.float64 and a.is_contiguous()
+                return ctypes.c_void_p(a.data_ptr()), a
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            return ctypes.c_void_p(a.ctypes.data), a
+
+        px, Xc = hp(Xc)
+        pz, Z = hp(Z)
+        pt, theta = hp(theta)
+        pw, wts = hp(wts)
+        pb, best = hp(best)
+        N = Xc.shape[0]
+        Lt, p = theta.shape
+        acq = None
+        if want_acq:
+            acq = out if out is not None else np.empty(N, dtype=np.float64)
+            pa = ctypes.c_void_p(acq.data_ptr() if isinstance(acq, torch.Tensor) else acq.ctypes.data)
+        else:
+            pa = None
+        tv = np.empty(max(k, 1), dtype=np.float64)
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        self._check(self.lib.bopl_uei_host(self.h, px, N, pz, Z.shape[0], UTILITY_KINDS[kind], pt, Lt, p, pw, pb, nH, pa,
+                                           k, int(index_offset), ctypes.c_void_p(tv.ctypes.data),
+                                           ctypes.c_void_p(ti.ctypes.data)))
+        if k:
+            return acq, tv[:k], ti[:k]
+        return acq

@@ -1,0 +1,331 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, via the drop-in classes) against the oracle on the same
+seeded inputs and the same common random numbers.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star: 1e-9 relative in fp64, identical argmax):
+  * posterior mean, acquisition values, gradients: |gpu - oracle| <= 1e-9 * max(|oracle|, scale) where scale is the
+    magnitude of the array (entries that are exactly or nearly zero — EI far from the incumbent — cannot be compared
+    relatively; two LAPACK builds do not agree on them either);
+  * posterior variance: |gpu - oracle| <= 1e-9 * |oracle| + 64 * floor, where floor is the change of the ORACLE's own
+    variance when its K* input is perturbed by one ulp, plus one ulp of the prior variance the column square-sum is
+    subtracted from (at cond(Ky) ~ 1e7 that alone exceeds 1e-9 relative for near-zero variances).
+    On the benchmark config S the floor term is not needed: plain 1e-9 relative.
+  * variance gradient (beta = -2 K* Winv cancels catastrophically at large cond(Ky)): 1e-9 * scale + 64 * the same
+    one-ulp-of-K* sensitivity of the oracle's own gradient.
+"""
+import numpy as np
+import pytest
+
+from bopl_b200.synthetic import make_problem
+from oracle import acquisition as oacq
+from tests.helpers import gpu_acquisition, gpu_model, oracle_model, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+CONFIGS = ["dtlz1a_linear", "dtlz2a_quad", "vlmop3_exp", "portfolio1"]
+
+
+def variance_floor(om, X):
+    """Sensitivity of the oracle's variance to a one-ulp perturbation of K(X, Xnew), per attribute: (m, N)."""
+    rs = np.random.RandomState(99)
+    out = []
+    for j in range(om.output_dim):
+        gp = om._cur(j)
+        Kx = gp.K(gp.X, X)
+        Kp = Kx * (1.0 + rs.choice([-1.0, 1.0], size=Kx.shape) * 2.0 ** -52)
+        from oracle.gp import dtrtrs
+        v0 = gp.variance - np.square(dtrtrs(gp.L, Kx)).sum(0)
+        v1 = gp.variance - np.square(dtrtrs(gp.L, Kp)).sum(0)
+        out.append(np.abs(v1 - v0) + 2.0 ** -52 * gp.variance)
+    return np.stack(out)
+
+
+def dvar_floor(om, X):
+    """Sensitivity of the oracle's variance gradient to a one-ulp perturbation of K(Xnew, X): (m, N, d)."""
+    from oracle.gp import kern_gradients_X
+    rs = np.random.RandomState(98)
+    out = []
+    for j in range(om.output_dim):
+        gp = om._cur(j)
+        Kx = gp.K(X, gp.X)
+        Kp = Kx * (1.0 + rs.choice([-1.0, 1.0], size=Kx.shape) * 2.0 ** -52)
+        g0 = kern_gradients_X(gp.kind, gp.variance, gp.lengthscale, -2.0 * np.dot(Kx, gp.Winv), X, gp.X)
+        g1 = kern_gradients_X(gp.kind, gp.variance, gp.lengthscale, -2.0 * np.dot(Kp, gp.Winv), X, gp.X)
+        out.append(np.abs(g1 - g0))
+    return np.stack(out)
+
+
+def check_dvar(got, om, X, what):
+    want = om.posterior_variance_gradient(X)
+    floor = dvar_floor(om, X)
+    tol = RTOL * np.maximum(np.abs(want), np.max(np.abs(want))) + 64 * (floor + np.max(floor, axis=(1, 2), keepdims=True) / 16)
+    err = np.abs(got - want)
+    assert np.all(err <= tol), "%s: worst err/tol %.3e" % (what, np.max(err / tol))
+
+
+def check_close(got, want, what, rtol=RTOL):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = float(np.max(np.abs(want))) if want.size else 0.0
+    err = np.abs(got - want)
+    tol = rtol * np.maximum(np.abs(want), scale)
+    assert np.all(err <= tol), "%s: max err %.3e (scale %.3e, rel-to-scale %.3e)" % (what, err.max(), scale, err.max() / max(scale, 1e-300))
+
+
+# ------------------------------------------------------------------------------------------------- posterior
+@pytest.mark.parametrize("name", CONFIGS)
+def test_posterior_named_configs(name):
+    p = make_problem(name)
+    om, gm = oracle_model(p), gpu_model(p)
+    X = p["Xc"]
+    mu_o, v_o = om.predict(X)
+    mu_g, v_g = gm.predict(X)
+    check_close(mu_g, mu_o, name + " mean")
+    floor = variance_floor(om, X)
+    assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + 1e-300), \
+        "%s var: worst excess %.3e" % (name, np.max(np.abs(v_g - v_o) - RTOL * np.abs(v_o) - 64 * floor))
+    # the separate entry points agree with predict
+    check_close(gm.posterior_mean(X), mu_o, name + " posterior_mean")
+    assert np.array_equal(gm.posterior_variance(X), v_g)
+    _, vn_o = om.predict_noiseless(X)
+    _, vn_g = gm.predict_noiseless(X)
+    assert np.all(np.abs(vn_g - vn_o) <= RTOL * np.abs(vn_o) + 64 * floor + 1e-300)
+    check_close(gm.posterior_mean_at_evaluated_points(), om.posterior_mean_at_evaluated_points(), name + " F")
+
+
+def test_posterior_config_S_plain_relative():
+    """Benchmark shape (n=2000, m=3, d=10), first 4096 candidates: plain 1e-9 relative on mean AND variance."""
+    p = make_problem("S", N=4096)
+    om, gm = oracle_model(p), gpu_model(p, gradients=False)
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    assert rel_err(v_g, v_o) < RTOL, rel_err(v_g, v_o)
+    check_close(mu_g, mu_o, "S mean")
+    assert scaled_err(mu_g, mu_o) < 1e-11
+
+
+@pytest.mark.parametrize("kind", ["Mat52", "rbf", "Mat32", "ExpQuad"])
+def test_cross_cov_kernels(kind):
+    p = make_problem("dtlz2a_quad", kind=kind, n=150, N=77)
+    om, gm = oracle_model(p), gpu_model(p)
+    eng = gm.engine
+    Xd = eng.to_dev(p["Xc"])
+    for j in range(p["m"]):
+        K_g = eng.cross_cov_dev(Xd, 0, j).cpu().numpy()
+        K_o = om.gps[j][0].K(p["Xc"], p["X"])
+        assert np.max(np.abs(K_g - K_o)) <= 1e-13 * p["variance"][j, 0], kind
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    check_close(mu_g, mu_o, kind + " mean")
+    floor = variance_floor(om, p["Xc"])
+    assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + 1e-300)
+
+
+@pytest.mark.parametrize("n,N", [(1, 1), (5, 3), (127, 129), (128, 128), (129, 1), (300, 257), (513, 1000)])
+def test_posterior_ragged_shapes(n, N):
+    """Training sets that are not multiples of the 128-row block, candidate counts that are not multiples of the tile."""
+    p = make_problem("portfolio1", n=n, N=N)
+    om, gm = oracle_model(p), gpu_model(p)
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    check_close(mu_g, mu_o, "mean n=%d N=%d" % (n, N))
+    floor = variance_floor(om, p["Xc"])
+    assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + 1e-300)
+
+
+def test_empty_batch_and_1d_input():
+    p = make_problem("dtlz1a_linear")
+    gm = gpu_model(p)
+    mu, v = gm.predict(np.empty((0, p["d"])))
+    assert mu.shape == (p["m"], 0) and v.shape == (p["m"], 0)
+    mu1, v1 = gm.predict(p["Xc"][0])                    # 1-D input is promoted (multi_outputGP.py:95)
+    mu2, v2 = gm.predict(p["Xc"][:1])
+    assert np.array_equal(mu1, mu2) and np.array_equal(v1, v2)
+
+
+def test_variance_clip_and_noise_at_training_points():
+    """At the evaluated points the raw variance is ~0: the 1e-10 clip (gpmodel.py:214) and the noise term apply."""
+    p = make_problem("dtlz2a_quad")
+    om, gm = oracle_model(p), gpu_model(p)
+    _, v_g = gm.predict_noiseless(p["X"])
+    assert np.all(v_g >= 1e-10)
+    _, v_n = gm.predict(p["X"])
+    assert np.all(v_n >= 1e-10)
+    mu_g = gm.posterior_mean(p["X"])
+    check_close(mu_g, om.posterior_mean(p["X"]), "mean at train")
+
+
+def test_hyper_samples_select():
+    p = make_problem("dtlz1a_linear", H=3)
+    om, gm = oracle_model(p), gpu_model(p)
+    for h in range(3):
+        om.set_hyperparameters(h)
+        gm.set_hyperparameters(h)
+        mu_o, v_o = om.predict(p["Xc"])
+        mu_g, v_g = gm.predict(p["Xc"])
+        check_close(mu_g, mu_o, "mean h=%d" % h)
+        floor = variance_floor(om, p["Xc"])
+        assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + 1e-300)
+        check_close(gm.posterior_mean_at_evaluated_points(), om.posterior_mean_at_evaluated_points(), "F h=%d" % h)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_posterior_gradients(name):
+    p = make_problem(name, N=70)
+    om, gm = oracle_model(p), gpu_model(p)
+    check_close(gm.posterior_mean_gradient(p["Xc"]), om.posterior_mean_gradient(p["Xc"]), name + " dmean")
+    check_dvar(gm.posterior_variance_gradient(p["Xc"]), om, p["Xc"], name + " dvar")
+    # the L-BFGS shape: one to four points (GEMV path)
+    for k in (1, 3):
+        check_dvar(gm.posterior_variance_gradient(p["Xc"][:k]), om, p["Xc"][:k], name + " dvar N=%d" % k)
+
+
+# ------------------------------------------------------------------------------------------------- acquisition
+@pytest.mark.parametrize("name", CONFIGS)
+def test_uei_value_named_configs(name):
+    p = make_problem(name)
+    om, gm = oracle_model(p), gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    got = acq._compute_acq(p["Xc"])
+    marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], 1)
+    want = oacq.aggregate(marg, p["use_full_support"], p["prob"])
+    assert got.shape == (p["N"], 1)
+    check_close(got, want, name + " uEI")
+    assert np.argmax(got) == np.argmax(want)
+    # sign convention of the optimizer-facing call (base.py:40)
+    assert np.array_equal(acq.acquisition_function(p["Xc"]), -got)
+
+
+@pytest.mark.parametrize("name", ["dtlz1a_linear", "vlmop3_exp"])
+def test_uei_value_vs_loop_faithful_oracle(name):
+    """Against the statement-by-statement restatement of uEI._marginal_acq_parallel (tiny shapes)."""
+    from oracle import utilities
+    p = make_problem(name, N=24, n=30, n_w=7, L=4)
+    om, gm = oracle_model(p), gpu_model(p)
+    func, _ = utilities.get(p["utility"], p["m"])
+    marg = oacq.uei_marginal_loop(om, func, p["theta"], p["Z"], p["Xc"], 1, incumbent="per_h")
+    want = oacq.aggregate(marg, False, None)
+    acq = gpu_acquisition(p, gm)
+    check_close(acq._compute_acq(p["Xc"]), want, name + " uEI loop")
+
+
+def test_uei_hyper_samples_and_incumbent_quirk():
+    """H = 3: the batch path takes per-h incumbents (uEI.py:93,104), the single-point path the stale one (uEI.py:67)."""
+    p = make_problem("dtlz1a_linear", H=3, N=50)
+    om, gm = oracle_model(p), gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    marg = oacq.uei_marginal_vec(om, "linear", p["theta"], p["Z"], p["Xc"], 3, incumbent="per_h")
+    check_close(acq._compute_acq(p["Xc"]), oacq.aggregate(marg, False, None), "uEI H=3 batch")
+    assert gm._h == 2                                   # the reference leaves the model at h = n_h - 1
+    # single point: stale incumbent under the current h (= 2 now)
+    om.set_hyperparameters(2)
+    marg1 = oacq.uei_marginal_vec(om, "linear", p["theta"], p["Z"], p["Xc"][:1], 3, incumbent="stale")
+    check_close(acq._compute_acq(p["Xc"][:1]), oacq.aggregate(marg1, False, None), "uEI H=3 single")
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_uei_gradient(name):
+    p = make_problem(name, N=12)
+    om, gm = oracle_model(p), gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    f, df = acq._compute_acq_withGradients(p["Xc"])
+    marg, dmarg = oacq.uei_marginal_with_gradient_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], 1)
+    check_close(f, oacq.aggregate(marg, p["use_full_support"], p["prob"]), name + " uEI f")
+    check_close(df, oacq.aggregate_gradient(dmarg, p["use_full_support"], p["prob"]), name + " uEI df", rtol=1e-8)
+    f2, df2 = acq.acquisition_function_withGradients(p["Xc"][:1])     # the L-BFGS call shape
+    assert f2.shape == (1, 1) and df2.shape == (1, p["d"])
+    assert np.allclose(f2, -f[:1], rtol=1e-12, atol=0) and np.allclose(df2, -df[:1], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", ["dtlz1a_linear", "portfolio1"])
+def test_uei_affine(name):
+    from bopl_b200.acquisition import uEI_affine
+    p = make_problem(name, N=300, H=2)
+    om, gm = oracle_model(p), gpu_model(p)
+    acq = gpu_acquisition(p, gm, cls=uEI_affine)
+    want = oacq.aggregate(oacq.uei_affine_marginal_vec(om, p["theta"], p["Xc"], 2), False, None)
+    check_close(acq._compute_acq(p["Xc"]), want, name + " uEI_affine")
+    Xs = p["Xc"][:9]
+    marg, dmarg = oacq.uei_affine_marginal_with_gradient_loop(om, p["theta"], Xs, 2)
+    f, df = acq._compute_acq_withGradients(Xs)
+    check_close(f, oacq.aggregate(marg, False, None), name + " affine f")
+    check_close(df, oacq.aggregate_gradient(dmarg, False, None), name + " affine df", rtol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------- anchors / top-k
+def test_topk_matches_stable_argsort_with_ties_and_nan():
+    import torch
+    from bopl_b200.engine import Engine
+    eng = Engine(0)
+    rs = np.random.RandomState(0)
+    for N, k in [(1, 1), (20, 20), (2048, 20), (2049, 7), (100000, 20), (300000, 256)]:
+        a = rs.normal(size=N)
+        a[rs.randint(0, N, size=N // 3)] = 0.0           # exact ties (EI == 0 is common)
+        if N > 50:
+            a[rs.randint(0, N, size=5)] = np.nan
+            a[rs.randint(0, N, size=5)] = a.max() if np.isfinite(a.max()) else 1.0
+        val, idx = eng.topk_dev(eng.to_dev(a), k, index_offset=1000)
+        scores = -a
+        scores[np.isnan(scores)] = np.inf                 # np.argsort puts NaN last
+        want = np.argsort(scores, kind="stable")[:k]
+        assert np.array_equal(idx.cpu().numpy() - 1000, want), (N, k)
+        got_v = val.cpu().numpy()
+        assert np.array_equal(got_v[~np.isnan(got_v)], a[want][~np.isnan(a[want])])
+
+
+def test_anchor_generator_fused_path_matches_argsort():
+    from bopl_b200.anchor_points import BoxSpace, ObjectiveAnchorPointsGenerator
+    p = make_problem("dtlz2a_quad", N=3000)
+    om, gm = oracle_model(p), gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    gen = ObjectiveAnchorPointsGenerator(BoxSpace([(0, 1)] * p["d"]), "random", acq.acquisition_function, p["N"])
+    anchors, scores = gen.select(p["Xc"], 20, get_scores=True)
+    marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], 1)
+    want = oacq.aggregate(marg, True, p["prob"])[:, 0]
+    idx, sc = oacq.top_k(-want, 20)
+    pos = want[idx] > 1e-12 * want.max()                  # identity of the anchors wherever the value is not a tie at 0
+    assert np.array_equal(anchors[pos], p["Xc"][idx][pos])
+    check_close(scores, sc, "anchor scores")
+    assert np.array_equal(anchors[0], p["Xc"][np.argmax(want)])
+
+
+def test_host_path_chunking_equals_device_path_and_is_permutation_invariant():
+    """N larger than one host chunk (148*128*8 candidates): chunked/overlapped host path == one-launch device path,
+    bit for bit; scoring a permuted batch permutes the scores, bit for bit (size-independent property)."""
+    p = make_problem("dtlz1a_linear", N=400000, n=40)
+    gm = gpu_model(p, gradients=False)
+    acq = gpu_acquisition(p, gm)
+    eng = gm.engine
+    a_host = acq._compute_acq(p["Xc"])[:, 0]
+    kind, theta, th_d, wts, best = acq._prepare(per_h=True)
+    a_dev = eng.uei_dev(eng.to_dev(p["Xc"]), eng.to_dev(p["Z"]), kind, th_d, eng.to_dev(wts), best, 1).cpu().numpy()
+    assert np.array_equal(a_host, a_dev)
+    perm = np.random.RandomState(5).permutation(p["N"])
+    a_perm = acq._compute_acq(p["Xc"][perm])[:, 0]
+    assert np.array_equal(a_perm, a_host[perm])
+    assert np.all(a_host >= 0.0)
+    val, idx = acq.top_candidates(p["Xc"], 20)
+    want = np.argsort(-a_host, kind="stable")[:20]
+    assert np.array_equal(idx, want) and np.array_equal(val, a_host[want])
+
+
+# ------------------------------------------------------------------------------------------------- error behaviour
+def test_errors_are_loud():
+    from bopl_b200 import BoplError
+    from bopl_b200.utility import Utility, UtilityDistribution
+    p = make_problem("dtlz1a_linear")
+    gm = gpu_model(p, gradients=False)
+    with pytest.raises(BoplError):
+        gm.posterior_variance_gradient(p["Xc"][:2])      # no Winv uploaded
+    acq = gpu_acquisition(p, gm)
+    with pytest.raises(BoplError):
+        acq._compute_acq_withGradients(p["Xc"][:2])
+    acq.utility_parameter_samples = p["theta"][:, :1]     # wrong parameter width for a linear utility
+    with pytest.raises(BoplError):
+        acq._compute_acq(p["Xc"])
+    dist = UtilityDistribution(support=p["theta"], prob_dist=np.ones(len(p["theta"])) / len(p["theta"]))
+    weird = Utility(func=lambda y, t: np.sin(np.dot(t, y)), parameter_distribution=dist)
+    with pytest.raises(NotImplementedError):
+        weird.resolve_kind(p["m"], p["theta"][0])
+    with pytest.raises(ValueError):
+        gm.predict(np.zeros((3, p["d"] + 1)))
