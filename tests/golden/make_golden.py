@@ -254,7 +254,7 @@ CASES = [  # name, kwargs for make_problem, experiment script providing the util
     ("dtlz1a_linear", dict(N=12, n=30, n_w=6, L=4, H=2), "test_dtlz1a_linear.py"),
     ("dtlz2a_quad", dict(N=12, n=30, n_w=6, L=8, H=2), "test_dtlz2a_quad.py"),
     ("vlmop3_exp", dict(N=12, n=30, n_w=6, L=4, H=2), "test_vlmop3_exp.py"),
-    ("portfolio1", dict(N=12, n=30, n_w=6, L=4, H=1), "test_dtlz1a_linear.py"),
+    ("portfolio1", dict(N=60, n=30, n_w=6, L=4, H=1), "test_dtlz1a_linear.py"),
 ]
 
 

@@ -329,3 +329,54 @@ def test_errors_are_loud():
         weird.resolve_kind(p["m"], p["theta"][0])
     with pytest.raises(ValueError):
         gm.predict(np.zeros((3, p["d"] + 1)))
+
+
+# ------------------------------------------------------------------------------------------------- golden fixtures
+def _golden(prefix):
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(f for f in os.listdir(gdir) if f.startswith(prefix) and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("fname", _golden("uEI_"))
+def test_cuda_path_against_reference_generated_golden(fname):
+    """The CUDA path against outputs of the reference's OWN code (tests/golden/make_golden.py), not via the oracle."""
+    import os
+    from bopl_b200.acquisition import uEI_affine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname), allow_pickle=False)
+    name, H = str(g["name"]), int(g["H"])
+    p = make_problem(name, N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=H)
+    gm = gpu_model(p)
+    X = p["Xc"]
+    if str(g["acq"]) == "uEI":
+        om = oracle_model(p)
+        for h in range(H):
+            gm.set_hyperparameters(h)
+            om.set_hyperparameters(h)
+            mu, var = gm.predict(X)
+            check_close(mu, g["mean_h%d" % h], fname + " mean")
+            floor = variance_floor(om, X)
+            assert np.all(np.abs(var - g["var_h%d" % h]) <= RTOL * np.abs(var) + 64 * floor)
+            assert np.all(np.abs(gm.predict_noiseless(X)[1] - g["var_noiseless_h%d" % h]) <= RTOL * np.abs(var) + 64 * floor)
+            check_close(gm.posterior_mean_gradient(X), g["dmean_h%d" % h], fname + " dmean")
+            dv, fl = g["dvar_h%d" % h], dvar_floor(om, X)
+            tol = RTOL * np.maximum(np.abs(dv), np.abs(dv).max()) + 64 * (fl + np.max(fl, axis=(1, 2), keepdims=True) / 16)
+            assert np.all(np.abs(gm.posterior_variance_gradient(X) - dv) <= tol)
+            check_close(gm.posterior_mean_at_evaluated_points(), g["F_h%d" % h], fname + " F")
+        acq = gpu_acquisition(p, gm)
+        gm.set_hyperparameters(0)
+        check_close(acq._compute_acq(X, parallel=False), g["acq_sequential"], fname + " sequential")
+        gm.set_hyperparameters(0)
+        check_close(acq._compute_acq(X, parallel=True), g["acq_parallel"], fname + " parallel")
+        gm.set_hyperparameters(0)
+        f, df = acq._compute_acq_withGradients(X)
+        check_close(f, g["acq_grad_f"], fname + " grad f")
+        check_close(df, g["acq_grad_df"], fname + " grad df", rtol=1e-7)
+        if g["acq_parallel"].max() > 0:
+            assert np.argmax(acq._compute_acq(X)) == np.argmax(g["acq_parallel"])
+    else:
+        acq = gpu_acquisition(p, gm, cls=uEI_affine)
+        check_close(acq._compute_acq(X), g["acq_value"], fname + " affine value")
+        f, df = acq._compute_acq_withGradients(X)
+        check_close(f, g["acq_grad_f"], fname + " affine f")
+        check_close(df, g["acq_grad_df"], fname + " affine df", rtol=1e-7)

@@ -1,0 +1,179 @@
+"""CPU tests of the host-side logic: C-ABI library exports, utility objects, anchor selection, sharding helpers,
+state extraction.  No compute call touches a GPU here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bopl_b200 import _lib
+from bopl_b200.anchor_points import (BoxSpace, ObjectiveAnchorPointsGenerator, samples_multidimensional_uniform)
+from bopl_b200.sharding import merge_topk, pack_records, shard_bounds
+from bopl_b200.synthetic import make_problem
+from bopl_b200.utility import Utility, UtilityDistribution, infer_kind, preference_encoder
+from oracle import utilities
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    _lib.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "bopl_b200.h")).read()
+    declared = set(re.findall(r"\b(bopl_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.bopl_build_info()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.bopl_create(ctypes.byref(h), 0)
+    assert rc != 0 and not h
+    assert b"no CUDA device" in lib.bopl_last_error(None)
+    from bopl_b200.engine import Engine
+    with pytest.raises(_lib.BoplError):
+        Engine(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bopl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+@pytest.mark.parametrize("kind,m,theta", [("linear", 3, [0.2, 0.3, 0.5]), ("quadratic", 4, [0.1, -0.4, 0.3, 1.0]),
+                                           ("exponential", 3, [0.25])])
+def test_utility_kind_inference(kind, m, theta):
+    func, grad = utilities.get(kind, m)
+    assert infer_kind(func, m, np.array(theta)) == kind
+    u = Utility(func=func, gradient=grad, parameter_distribution=None)
+    assert u.resolve_kind(m, np.array(theta)) == kind
+    y = np.random.RandomState(0).normal(size=m)
+    assert np.allclose(u.eval_func(y, np.array(theta)), func(y, np.array(theta)))
+
+
+def test_utility_kind_inference_rejects_unknown_callable():
+    with pytest.raises(NotImplementedError):
+        infer_kind(lambda y, t: np.tanh(np.dot(t, y)), 3, np.ones(3))
+    with pytest.raises(ValueError):
+        Utility(func=None, kind="cubic")
+
+
+def test_utility_distribution_full_support_rule_and_sampling():
+    sup = np.arange(24.0).reshape(8, 3)
+    d = UtilityDistribution(support=sup, prob_dist=np.ones(8) / 8)
+    assert d.use_full_support                                    # < 20 support points (utility_distribution.py:27-30)
+    d2 = UtilityDistribution(support=np.zeros((25, 3)), prob_dist=np.ones(25) / 25)
+    assert not d2.use_full_support
+    np.random.seed(3)
+    s = d.sample(5)
+    assert s.shape == (5, 3) and all(any(np.array_equal(r, q) for q in sup) for r in s)
+    a = d.sample_from_prior(4, seed=7)
+    b = d.sample_from_prior(4, seed=7)
+    assert np.array_equal(a, b)
+    with pytest.raises(Exception):
+        UtilityDistribution()
+
+
+def test_utility_distribution_preference_updates():
+    func, _ = utilities.get("linear", 2)
+    sup = np.array([[1.0, 0.0], [0.0, 1.0], [0.5, 0.5]])
+    pair = [np.array([1.0, 0.0]), np.array([0.0, 1.0])]
+    d = UtilityDistribution(support=sup.copy(), prob_dist=np.ones(3) / 3, utility_func=func,
+                            elicitation_strategy=lambda Y: [pair[0], pair[1]])
+    d.add_preference_information(lambda y: y[0], None, 1)        # the true utility prefers the first item
+    assert np.array_equal(d.support, sup[:1]) and np.allclose(d.prob_dist, [1.0])
+    assert d.preference_information[0][2] == 1
+    # prior sampler + rejection
+    rs = np.random.RandomState(0)
+    gen = lambda n, seed=None: rs.dirichlet(np.ones(2), n)
+    d3 = UtilityDistribution(prior_sample_generator=gen, utility_func=func, elicitation_strategy=lambda Y: [pair[0], pair[1]])
+    d3.add_preference_information(lambda y: y[0], None, 1)
+    th = d3.sample(6)
+    assert th.shape == (6, 2) and np.all(th[:, 0] > th[:, 1])
+    assert preference_encoder(1.0, 1.0) == 0 and preference_encoder(0.0, 1.0) == -1
+
+
+def test_candidate_generator_matches_reference_draw():
+    bounds = [(-3.0, 3.0), (0.0, 1.0)]
+    a = samples_multidimensional_uniform(bounds, 7, seed=11)
+    z = np.random.RandomState(11).uniform(size=(7, 2))
+    assert np.array_equal(a, np.stack([6 * z[:, 0] - 3, z[:, 1]], axis=1))
+    np.random.seed(5)
+    b = samples_multidimensional_uniform(bounds, 3)
+    np.random.seed(5)
+    assert np.array_equal(b[:, 1], np.random.uniform(size=(3, 2))[:, 1])
+
+
+def test_anchor_generator_host_path_is_stable_argsort():
+    space = BoxSpace([(0, 1)] * 2)
+    X = np.random.RandomState(0).uniform(size=(50, 2))
+    scores = np.round(X[:, 0], 1)                                # many exact ties
+    gen = ObjectiveAnchorPointsGenerator(space, "random", lambda Z: np.round(Z[:, :1], 1), 50)
+    anchors, sc = gen.select(X, 5, get_scores=True)
+    order = np.argsort(scores, kind="stable")[:5]
+    assert np.array_equal(anchors, X[order]) and np.array_equal(sc, scores[order])
+    np.random.seed(1)
+    out = gen.get(num_anchor=60)
+    assert out.shape == (50, 2)                                  # min(len(scores), num_anchor)
+
+
+def test_shard_bounds_cover_and_balance():
+    for N, G in [(10, 3), (2 ** 20, 8), (5, 8), (0, 2)]:
+        blocks = [shard_bounds(N, G, r) for r in range(G)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == N
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(G - 1))
+        sizes = [e - s for s, e in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_merge_topk_is_deterministic_value_then_index():
+    vals = np.array([[3.0, 1.0, 0.0], [3.0, 2.0, np.nan], [0.0, 0.0, 0.0]])
+    idxs = np.array([[10, 11, 12], [5, 6, 7], [1, 2, 3]])
+    v, i, pos = merge_topk(vals, idxs, 6)
+    assert i.tolist() == [5, 10, 6, 11, 1, 2] and v.tolist() == [3.0, 3.0, 2.0, 1.0, 0.0, 0.0]
+    rec = pack_records(np.array([1.5]), np.array([2 ** 40 + 3]), np.array([[0.25, 0.5]]), 3)
+    assert rec.shape == (3, 4) and int(rec[0, 1]) == 2 ** 40 + 3 and np.isnan(rec[1:, 0]).all()
+
+
+def test_state_extractor_on_reference_shaped_objects():
+    """`state_from_reference_model` reads the reference's live-object fields; here they are plain
+    namespaces filled by the product's own host fit, and the round trip must be the identity."""
+    from types import SimpleNamespace as NS
+    from bopl_b200.models import state_from_hyperparameters, state_from_reference_model
+    p = make_problem("dtlz1a_linear", n=12, H=2)
+    st = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"])
+    outs = []
+    for j in range(st.m):
+        insts = [NS(X=st.X, kern=NS(name=st.kinds[j, h], variance=np.array([st.variance[j, h]]), lengthscale=st.lengthscale[j, h]),
+                    likelihood=NS(variance=np.array([st.noise[j, h]])), normalizer=NS(mean=np.array([st.ymean[j, h]])),
+                    posterior=NS(_woodbury_chol=np.asfortranarray(st.L[j, h]), woodbury_vector=st.alpha[j, h][:, None],
+                                 woodbury_inv=st.Winv[j, h])) for h in range(st.H)]
+        outs.append(NS(model_instances=insts))
+    st2 = state_from_reference_model(NS(output_dim=st.m, output=outs))
+    for f in ("X", "lengthscale", "variance", "noise", "ymean", "L", "alpha", "Winv"):
+        assert np.array_equal(getattr(st, f), getattr(st2, f)), f
+    assert (st.kinds == st2.kinds).all()
+
+
+def test_host_fit_matches_oracle_fit():
+    """The product's LAPACK fit (models.fit_exact_gp) and the oracle's are independent restatements of
+    exact_gaussian_inference.py:44-51; they must agree to rounding."""
+    from bopl_b200.models import fit_exact_gp
+    from oracle.gp import ExactGP
+    p = make_problem("vlmop3_exp", n=40)
+    for j in range(p["m"]):
+        L, alpha, ymean, Winv = fit_exact_gp(p["X"], p["Y"][j], "Mat52", p["variance"][j, 0], p["lengthscale"][j, 0], p["noise"][j, 0])
+        g = ExactGP(p["X"], p["Y"][j], "Mat52", p["variance"][j, 0], p["lengthscale"][j, 0], p["noise"][j, 0])
+        assert np.allclose(L, np.tril(g.L), rtol=1e-12, atol=1e-14)
+        assert np.allclose(alpha, g.alpha[:, 0], rtol=1e-9) and ymean == g.ymean
+        assert np.allclose(Winv, g.Winv, rtol=1e-9, atol=1e-9 * np.abs(g.Winv).max())

@@ -184,6 +184,21 @@ def test_oracle_against_reference_generated_golden(fname):
     om = oracle_model(p)
     full, prob = bool(g["use_full_support"]), (g["prob"] if g["prob"].size else None)
     if str(g["acq"]) == "uEI":
+        # posterior layer: the reference's MultiOutputGP -> GPModel -> GP -> PosteriorExact -> Stationary code
+        for h in range(H):
+            om.set_hyperparameters(h)
+            mu, var = om.predict(p["Xc"])
+            assert np.allclose(mu, g["mean_h%d" % h], rtol=1e-11, atol=1e-12 * np.abs(mu).max())
+            assert np.allclose(om.posterior_mean(p["Xc"]), g["pmean_h%d" % h], rtol=1e-11, atol=1e-12 * np.abs(mu).max())
+            vtol = 1e-9 * np.abs(var).max()
+            assert np.allclose(var, g["var_h%d" % h], rtol=1e-9, atol=vtol)
+            assert np.allclose(om.posterior_variance(p["Xc"]), g["pvar_h%d" % h], rtol=1e-9, atol=vtol)
+            assert np.allclose(om.predict_noiseless(p["Xc"])[1], g["var_noiseless_h%d" % h], rtol=1e-9, atol=vtol)
+            dm, dv = om.posterior_mean_gradient(p["Xc"]), om.posterior_variance_gradient(p["Xc"])
+            assert np.allclose(dm, g["dmean_h%d" % h], rtol=1e-9, atol=1e-11 * np.abs(dm).max())
+            assert np.allclose(dv, g["dvar_h%d" % h], rtol=1e-7, atol=1e-8 * np.abs(dv).max())
+            F = om.posterior_mean_at_evaluated_points()
+            assert np.allclose(F, g["F_h%d" % h], rtol=1e-11, atol=1e-12 * np.abs(F).max())
         om.set_hyperparameters(0)
         marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], H, incumbent="stale")
         assert np.allclose(oacq.aggregate(marg, full, prob), g["acq_sequential"], rtol=1e-11, atol=1e-13)
