@@ -2,6 +2,7 @@
 // that sequence the kernels.  Plain pointers and sizes only; every entry returns a bopl_status.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -155,6 +156,8 @@ int bopl_create(bopl_handle** out, int device) {
   bopl_handle* h = new bopl_handle();
   h->device = device;
   h->sms = prop.multiProcessorCount;
+  if (const char* v = getenv("BOPL_TRSM_VARIANT")) h->trsm_variant = atoi(v);
+  if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
@@ -174,7 +177,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {

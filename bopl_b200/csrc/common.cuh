@@ -12,7 +12,7 @@
 namespace bopl {
 
 constexpr int TRSM_BM = 128;   // rows of L per block row (= diagonal block size)
-constexpr int TRSM_BC = 128;   // candidates per tile
+constexpr int TRSM_BC = 128;   // candidate granule of the host-path chunking (both tile widths divide it)
 constexpr int TRSM_BK = 16;    // k-depth of one pipeline stage
 constexpr int MAX_D = 24;      // input dimensions the shared-memory staging is sized for
 constexpr int MAX_M = 16;      // attributes
@@ -41,6 +41,9 @@ struct bopl_handle {
   bool has_model = false, has_winv = false;
   std::string err;
   long long launches = 0;
+  int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
+  int* sm_slots = nullptr;
+  int trsm_variant = 1;                // 1: 128x128 tiles, one CTA per SM (default); 2: 128x64 tiles, two CTAs per SM (BOPL_TRSM_VARIANT=2)
   // model storage
   std::vector<void*> owned;            // every cudaMalloc'ed model buffer
   bopl::GpDev* gp_dev = nullptr;       // [m*H] device array, index j*H + h
@@ -111,39 +114,162 @@ int launch_topk(bopl_handle* h, const double* acq, int N, int k, long long index
                 cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- device math
+// Branch-free fp64 sqrt and exp for the cross-covariance.  CUDA's libm versions carry slow-path branches (denormals,
+// overflow), which keep the compiler from interleaving the independent evaluations of neighbouring kernel entries;
+// K* generation was latency-bound because of it (profiles/r01_trsm_v1_ncu.md).  Both are accurate to ~1 ulp over the
+// ranges the kernels produce (checked against the oracle at 1e-13 in tests/test_gpu_parity.py::test_cross_cov_kernels).
+
+// sqrt(a) for a >= 0 (0 and denormals -> 0): MUFU.RSQ64H seed (2^-22.9), two Newton steps on 1/sqrt, one on sqrt.
+__device__ __forceinline__ double sqrt_nonneg(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h, y * y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h, y * y, 0.5);
+  y = fma(y, e, y);
+  double r = a * y;
+  r = fma(fma(-r, r, a), 0.5 * y, r);
+  return (a >= 1e-300) ? r : 0.0;
+}
+
+// exp(x) for x <= 0 (clamped at -700: the result is then ~1e-304 instead of a denormal or 0).
+// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2; degree-13 Taylor polynomial (remainder 4e-18); exponent insertion.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  x = fmax(x, -700.0);
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest integer in the low word
+  double kd = fma(x, 1.4426950408889634074, magic);
+  const int k = __double2loint(kd);
+  kd -= magic;
+  double r = fma(kd, -0x1.62e42fee00000p-1, x);
+  r = fma(kd, -0x1.a39ef35793c76p-33, r);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // Stationary kernels as functions of the squared scaled distance r2 (already clipped at 0).
 // K_of_r: GPy/kern/src/stationary.py:529-530 (Mat52), :440-441 (Mat32), :594-595 (ExpQuad); rbf.py:42-43.
 __device__ __forceinline__ double kern_value(int kind, double variance, double r2) {
   if (kind == BOPL_KERN_MAT52) {
     const double s5 = 2.23606797749978969641;
-    double r = sqrt(r2);
-    return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp(-s5 * r);
+    double r = sqrt_nonneg(r2);
+    return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp_nonpos(-s5 * r);
   } else if (kind == BOPL_KERN_MAT32) {
     const double s3 = 1.73205080756887729353;
-    double r = sqrt(r2);
-    return variance * (1.0 + s3 * r) * exp(-s3 * r);
+    double r = sqrt_nonneg(r2);
+    return variance * (1.0 + s3 * r) * exp_nonpos(-s3 * r);
   } else {
-    double r = sqrt(r2);
-    return variance * exp(-0.5 * (r * r));
+    double r = sqrt_nonneg(r2);
+    return variance * exp_nonpos(-0.5 * (r * r));
   }
+}
+
+// Eight kernel values at once, written operation-by-operation across the eight lanes so that the eight independent
+// sqrt / exp dependency chains interleave in the instruction stream (the same arithmetic as kern_value).
+__device__ __forceinline__ void kern_value8(int kind, double variance, const double* r2, double* out) {
+  double r[8], x[8], pre[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2[u]));
+    r[u] = y;
+  }
+  {
+    double h[8], e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) h[u] = 0.5 * r2[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = fma(-h[u], r[u] * r[u], 0.5);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = fma(r[u], e[u], r[u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = fma(-h[u], r[u] * r[u], 0.5);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = fma(r[u], e[u], r[u]);      // 1/sqrt
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = r2[u] * r[u];                // sqrt estimate
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = fma(fma(-e[u], e[u], r2[u]), 0.5 * r[u], e[u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = (r2[u] >= 1e-300) ? e[u] : 0.0;
+  }
+  if (kind == BOPL_KERN_MAT52) {
+    const double s5 = 2.23606797749978969641;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      pre[u] = variance * (1.0 + s5 * r[u] + (5.0 / 3.0) * (r[u] * r[u]));
+      x[u] = -s5 * r[u];
+    }
+  } else if (kind == BOPL_KERN_MAT32) {
+    const double s3 = 1.73205080756887729353;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      pre[u] = variance * (1.0 + s3 * r[u]);
+      x[u] = -s3 * r[u];
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      pre[u] = variance;
+      x[u] = -0.5 * (r[u] * r[u]);
+    }
+  }
+  int k[8];
+  const double magic = 6755399441055744.0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    x[u] = fmax(x[u], -700.0);
+    double kd = fma(x[u], 1.4426950408889634074, magic);
+    k[u] = __double2loint(kd);
+    kd -= magic;
+    double rr = fma(kd, -0x1.62e42fee00000p-1, x[u]);
+    x[u] = fma(kd, -0x1.a39ef35793c76p-33, rr);
+  }
+  double pl[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) pl[u] = fma(1.0 / 6227020800.0, x[u], 1.0 / 479001600.0);
+  const double c[11] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+                        1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+#pragma unroll
+  for (int s = 0; s < 11; ++s)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pl[u] = fma(pl[u], x[u], c[s]);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) pl[u] = fma(pl[u], x[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    out[u] = pre[u] * __hiloint2double(__double2hiint(pl[u]) + (k[u] << 20), __double2loint(pl[u]));
 }
 
 // value and g = (dK/dr)/r with 1/r := 0 at r == 0  (stationary.py:227-234 _inv_dist; dK_dr :532-533, :443-444, :597-598; rbf.py:45-46)
 __device__ __forceinline__ void kern_value_grad(int kind, double variance, double r2, double& k, double& g) {
-  double r = sqrt(r2);
+  double r = sqrt_nonneg(r2);
   double invr = (r != 0.0) ? 1.0 / r : 0.0;
   if (kind == BOPL_KERN_MAT52) {
     const double s5 = 2.23606797749978969641;
-    double e = exp(-s5 * r);
+    double e = exp_nonpos(-s5 * r);
     k = variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * e;
     g = variance * ((10.0 / 3.0) * r - 5.0 * r - (5.0 * s5 / 3.0) * (r * r)) * e * invr;
   } else if (kind == BOPL_KERN_MAT32) {
     const double s3 = 1.73205080756887729353;
-    double e = exp(-s3 * r);
+    double e = exp_nonpos(-s3 * r);
     k = variance * (1.0 + s3 * r) * e;
     g = -3.0 * variance * r * e * invr;
   } else {
-    k = variance * exp(-0.5 * (r * r));
+    k = variance * exp_nonpos(-0.5 * (r * r));
     g = -r * k * invr;
   }
 }
