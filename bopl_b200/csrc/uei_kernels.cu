@@ -17,9 +17,28 @@ constexpr int MC_WARPS = MC_NT / 32;
 
 // U(a, theta_l) for a in registers.  Utilities: experiments/test_dtlz1a_linear.py:51-55, test_dtlz2a_quad.py:51-57,
 // test_vlmop3_exp.py:41-52.
-template <int KIND>
+template <int KIND, int M = 0>
 __device__ __forceinline__ double utility_value(const double* a, const double* th, int m) {
   double u = 0.0;
+  if (M > 0) {   // compile-time attribute count: no predicated dead iterations in the (sample, theta) inner loop
+    if (KIND == BOPL_UTIL_LINEAR) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) u = fma(th[j], a[j], u);
+    } else if (KIND == BOPL_UTIL_QUADRATIC) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double df = a[j] - th[j];
+        u = fma(df, df, u);
+      }
+      u = -u;
+    } else {
+      const double t0 = th[0];
+#pragma unroll
+      for (int j = 0; j < M; ++j) u += 1.0 - exp(-t0 * a[j]);
+      u = u / t0 / (double)M;
+    }
+    return u;
+  }
   if (KIND == BOPL_UTIL_LINEAR) {
 #pragma unroll
     for (int j = 0; j < MAX_M; ++j)
@@ -76,11 +95,13 @@ __device__ __forceinline__ void stage_small(const McParams& p, double* zs, doubl
   __syncthreads();
 }
 
-// One warp per candidate.  The (k, l) pairs are flattened (pair = k*Lt + l) and dealt round-robin to the lanes so
-// any (nw, Lt) keeps all 32 lanes busy; each lane accumulates w_l * max(U - best_l, 0), then a butterfly shuffle sums
-// the lanes (xor pattern => every lane ends with the same, order-fixed, total).
-template <int KIND>
+// One warp per candidate; the lanes own the MC samples (k = lane, lane+32, ...): a lane forms its posterior sample
+// a = mu + sigma * Z_k once and then sweeps the utility parameters theta_l (broadcast reads from shared memory),
+// accumulating w_l * max(U(a, theta_l) - best_l, 0).  A butterfly shuffle sums the lanes (xor pattern => every lane ends
+// with the same, order-fixed, total).
+template <int KIND, int M>
 __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
+  constexpr int MM = (M > 0) ? M : MAX_M;
   extern __shared__ double sm[];
   double* zs = sm;
   double* ths = zs + p.nw * p.m;
@@ -90,24 +111,35 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * MC_WARPS;
-  const int m = p.m, npairs = p.nw * p.Lt;
+  const int m = (M > 0) ? M : p.m;
   for (int c = warp_global; c < p.N; c += nwarps) {
-    double mu[MAX_M], sg[MAX_M];
+    double mu[MM], sg[MM];
 #pragma unroll
-    for (int j = 0; j < MAX_M; ++j)
+    for (int j = 0; j < MM; ++j)
       if (j < m) {
         mu[j] = p.mean[(size_t)j * p.N + c];
         sg[j] = sqrt(p.var[(size_t)j * p.N + c]);
       }
     double acc = 0.0;
-    for (int pr = lane; pr < npairs; pr += 32) {
-      const int k = pr / p.Lt, l = pr - k * p.Lt;
-      double a[MAX_M];
+    for (int k = lane; k < p.nw; k += 32) {
+      double a[MM];
 #pragma unroll
-      for (int j = 0; j < MAX_M; ++j)
+      for (int j = 0; j < MM; ++j)
         if (j < m) a[j] = fma(sg[j], zs[k * m + j], mu[j]);
-      double u = utility_value<KIND>(a, ths + l * p.p, m);
-      acc = fma(ws[l], fmax(u - bs[l], 0.0), acc);
+      // two independent accumulation chains over theta (even / odd l), combined in a fixed order
+      double acc0 = 0.0, acc1 = 0.0;
+      int l = 0;
+      for (; l + 1 < p.Lt; l += 2) {
+        double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
+        double u1 = utility_value<KIND, M>(a, ths + (l + 1) * p.p, m);
+        acc0 = fma(ws[l], fmax(u0 - bs[l], 0.0), acc0);
+        acc1 = fma(ws[l + 1], fmax(u1 - bs[l + 1], 0.0), acc1);
+      }
+      if (l < p.Lt) {
+        double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
+        acc0 = fma(ws[l], fmax(u0 - bs[l], 0.0), acc0);
+      }
+      acc += acc0 + acc1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -115,6 +147,19 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
       double v = acc * p.scale;
       p.acq[c] = p.accumulate ? p.acq[c] + v : v;
     }
+  }
+}
+
+template <int KIND>
+void launch_mc_m(const McParams& mp, int grid, size_t smem, cudaStream_t st) {
+  switch (mp.m) {
+    case 1: uei_mc_kernel<KIND, 1><<<grid, MC_NT, smem, st>>>(mp); break;
+    case 2: uei_mc_kernel<KIND, 2><<<grid, MC_NT, smem, st>>>(mp); break;
+    case 3: uei_mc_kernel<KIND, 3><<<grid, MC_NT, smem, st>>>(mp); break;
+    case 4: uei_mc_kernel<KIND, 4><<<grid, MC_NT, smem, st>>>(mp); break;
+    case 5: uei_mc_kernel<KIND, 5><<<grid, MC_NT, smem, st>>>(mp); break;
+    case 6: uei_mc_kernel<KIND, 6><<<grid, MC_NT, smem, st>>>(mp); break;
+    default: uei_mc_kernel<KIND, 0><<<grid, MC_NT, smem, st>>>(mp); break;
   }
 }
 
@@ -325,9 +370,9 @@ int launch_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, 
   if (smem > 48 * 1024) return fail(h, BOPL_ERR_UNSUPPORTED, "uei_mc: nw*m + Lt*(p+2) exceeds 6144 doubles of shared staging");
   int grid = mc_grid(h, N);
   switch (util_kind) {
-    case BOPL_UTIL_LINEAR: uei_mc_kernel<BOPL_UTIL_LINEAR><<<grid, MC_NT, smem, st>>>(mp); break;
-    case BOPL_UTIL_QUADRATIC: uei_mc_kernel<BOPL_UTIL_QUADRATIC><<<grid, MC_NT, smem, st>>>(mp); break;
-    case BOPL_UTIL_EXPONENTIAL: uei_mc_kernel<BOPL_UTIL_EXPONENTIAL><<<grid, MC_NT, smem, st>>>(mp); break;
+    case BOPL_UTIL_LINEAR: launch_mc_m<BOPL_UTIL_LINEAR>(mp, grid, smem, st); break;
+    case BOPL_UTIL_QUADRATIC: launch_mc_m<BOPL_UTIL_QUADRATIC>(mp, grid, smem, st); break;
+    case BOPL_UTIL_EXPONENTIAL: launch_mc_m<BOPL_UTIL_EXPONENTIAL>(mp, grid, smem, st); break;
     default: return fail(h, BOPL_ERR_INVALID, "unknown utility kind");
   }
   BOPL_LAUNCH_CHECK(h, "uei_mc_kernel");
