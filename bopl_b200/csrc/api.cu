@@ -226,6 +226,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
 
   std::vector<double> Lp((size_t)n_pad * n_pad);
   std::vector<double> Dinv((size_t)nblk * TRSM_BM * TRSM_BM);
+  std::vector<double> DinvFrag((size_t)nblk * 136 * 64);
   std::vector<double> Xs((size_t)n_pad * d), al((size_t)n_pad);
   h->gp_host.resize((size_t)m * H);
   for (int g = 0; g < m * H; ++g) {
@@ -244,6 +245,8 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
         free_model(h);
         return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
       }
+    for (int b = 0; b < nblk; ++b)
+      pack_dinv_fragments(Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM, DinvFrag.data() + (size_t)b * 136 * 64);
     // negate the off-diagonal blocks so that the kernel's update is a pure accumulate: acc += (-L) V
     for (int i = 0; i < n_pad; ++i) {
       const int bi = i / TRSM_BM;
@@ -258,8 +261,9 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       al[pad + i] = alpha_h[(size_t)g * n + i];
     }
     GpDev gp{};
-    double *pL, *pD, *pX, *pa, *pe, *pW = nullptr;
+    double *pL, *pD, *pF, *pX, *pa, *pe, *pW = nullptr;
     if ((rc = dev_upload(h, Lp.data(), Lp.size(), &pL)) || (rc = dev_upload(h, Dinv.data(), Dinv.size(), &pD)) ||
+        (rc = dev_upload(h, DinvFrag.data(), DinvFrag.size(), &pF)) ||
         (rc = dev_upload(h, Xs.data(), Xs.size(), &pX)) || (rc = dev_upload(h, al.data(), al.size(), &pa)) ||
         (rc = dev_upload(h, ell, (size_t)d, &pe))) {
       free_model(h);
@@ -271,6 +275,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     }
     gp.Lneg = pL;
     gp.Dinv = pD;
+    gp.DinvFrag = pF;
     gp.Xs = pX;
     gp.alpha = pa;
     gp.ell = pe;

@@ -22,6 +22,7 @@ constexpr int MAX_TOPK = 256;
 struct GpDev {
   const double* Lneg;    // [n_pad*n_pad] front-padded factor, off-diagonal 128-blocks NEGATED (acc += (-L)·V); diagonal blocks unused
   const double* Dinv;    // [n_pad/128][128][128] inverses of the diagonal blocks (lower triangular)
+  const double* DinvFrag;  // [n_pad/128][136*64] the same inverses packed as DMMA B fragments (posterior_trsm_t.cu)
   const double* Xs;      // [n_pad*d] training inputs divided by the lengthscales, front-padded with zeros
   const double* alpha;   // [n_pad] woodbury vector, front-padded with zeros
   const double* Winv;    // [n*n] or nullptr
@@ -43,7 +44,8 @@ struct bopl_handle {
   long long launches = 0;
   int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
   int* sm_slots = nullptr;
-  int trsm_variant = 1;                // 1: 128x128 tiles, one CTA per SM (default); 2: 128x64 tiles, two CTAs per SM (BOPL_TRSM_VARIANT=2)
+  int trsm_variant = 3;                // BOPL_TRSM_VARIANT: 3 candidate-owning warps, diagonal solve in registers (default);
+                                       // 1 row-owning 128x128 tiles, one CTA per SM; 2 row-owning 128x64 tiles, two CTAs per SM
   // model storage
   std::vector<void*> owned;            // every cudaMalloc'ed model buffer
   bopl::GpDev* gp_dev = nullptr;       // [m*H] device array, index j*H + h
@@ -92,6 +94,9 @@ int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes);
 // launchers implemented in the kernel translation units
 int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                           cudaStream_t st);
+int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
+                            cudaStream_t st);
+void pack_dinv_fragments(const double* Dinv_block, double* out);
 int launch_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, cudaStream_t st);
 int launch_posterior_mean_strided(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, long long out_stride,
                                   cudaStream_t st);
