@@ -248,7 +248,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(N * 8 + K_ANCHOR * 16), "steps": e2e_steps,
                     "api": "bopl_uei_host via uEI.top_candidates (pinned host candidates -> scores + top-20 on the host)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "posterior_trsm_kernel (fused K*, FP64 DMMA blocked triangular solve, mean, variance)",
+            "roofline": {"bound": "tensor", "kernel": "posterior_trsm_t_kernel (fused K*, FP64 DMMA blocked triangular solve, mean, variance)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "kernel_ms": trsm_ms_avg, "flops_per_launch": flops_launch,
                          "peak_source": "profiles/r01_fp64_peaks.json: cuBLAS DGEMM 8192^3 measured on this pool's B200 "
