@@ -17,9 +17,12 @@ def __getattr__(name):
     if name in ("MultiOutputGP", "state_from_hyperparameters", "state_from_reference_model", "fit_exact_gp"):
         from . import models
         return getattr(models, name)
-    if name in ("uEI", "uEI_affine", "AcquisitionBase"):
+    if name in ("uEI", "uEI_affine", "uEI_constrained", "AcquisitionBase"):
         from . import acquisition
         return getattr(acquisition, name)
+    if name in ("AcquisitionOptimizer", "OptLbfgs", "apply_optimizer"):
+        from . import optimization
+        return getattr(optimization, name)
     if name in ("Engine", "GPState"):
         from . import engine
         return getattr(engine, name)

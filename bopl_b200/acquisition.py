@@ -3,6 +3,7 @@
   AcquisitionBase  GPyOpt/acquisitions/base.py:6-74          (sign flip; `optimize` hands f / f_df to the optimizer)
   uEI              bopl/sampling_policies/acquisition_functions/uEI.py:11-177
   uEI_affine       bopl/sampling_policies/acquisition_functions/uEI_affine.py:10-150
+  uEI_constrained  bopl/sampling_policies/acquisition_functions/uEI_constrained.py:8-164
 
 Same constructor signatures, attributes (`W_samples`, `utility_parameter_samples`, `utility_prob_dist`,
 `number_of_gp_hyps_samples`, `use_full_support`) and methods (`_compute_acq`, `_compute_acq_withGradients`,
@@ -183,6 +184,54 @@ class uEI_affine(_UtilityAcquisition):
         return self._run(X, True)
 
     def update_samples(self):                                            # uEI_affine.py:144-150
+        if self.use_full_support:
+            self.utility_parameter_samples = self.utility.parameter_distribution.support
+            self.utility_prob_dist = self.utility.parameter_distribution.prob_dist
+        else:
+            self.utility_parameter_samples = self.utility.sample_parameter(10)
+
+
+class uEI_constrained(_UtilityAcquisition):
+    """Closed-form constrained EI (uEI_constrained.py:8-164): EI of attribute 0 times the feasibility probabilities of
+    attributes 1.. against the thresholds theta.  As in the reference the incumbent ("max feasible value so far") is
+    computed ONCE, under the model's current hyper-sample, before the h-loop (uEI_constrained.py:52,98)."""
+
+    def __init__(self, model, space, optimizer=None, cost_withGradients=None, utility=None):
+        self.optimizer = optimizer
+        self.utility = utility
+        super(uEI_constrained, self).__init__(model, space, optimizer, cost_withGradients=cost_withGradients)
+        self.use_full_support = self.utility.parameter_distribution.use_full_support
+        self.number_of_gp_hyps_samples = min(10, self.model.number_of_hyps_samples())   # the reference hard-codes 10
+        if self.use_full_support:
+            self.utility_parameter_samples = self.utility.parameter_distribution.support
+            self.utility_prob_dist = self.utility.parameter_distribution.prob_dist
+        else:
+            self.utility_parameter_samples = self.utility.sample_parameter(10)
+
+    def _run(self, X, with_grad):
+        X = self._x(X)
+        eng = self.model.engine
+        n_h = self.number_of_gp_hyps_samples
+        theta = self._thetas()
+        if theta.shape[1] != self.model.output_dim - 1:
+            raise ValueError("uEI_constrained needs one threshold per constraint attribute (m - 1)")
+        kind = self.utility.resolve_kind(self.model.output_dim, theta[0])
+        if kind != "constrained":
+            raise NotImplementedError("uEI_constrained needs the threshold-constraint utility (kind='constrained')")
+        th_d = eng.to_dev(theta)
+        best = self._incumbents("constrained", th_d, per_h=False)
+        acq, dacq = eng.uei_constrained_dev(eng.to_dev(X), th_d, eng.to_dev(self._weights(len(theta))), best, n_h, with_grad)
+        self.model.set_hyperparameters(n_h - 1)
+        acq = acq.cpu().numpy().reshape(X.shape[0], 1)
+        return (acq, dacq.cpu().numpy().reshape(X.shape)) if with_grad else acq
+
+    def _compute_acq(self, X):
+        return self._run(X, False)
+
+    def _compute_acq_withGradients(self, X):
+        return self._run(X, True)
+
+    def update_samples(self):                                            # uEI_constrained.py:128-134
         if self.use_full_support:
             self.utility_parameter_samples = self.utility.parameter_distribution.support
             self.utility_prob_dist = self.utility.parameter_distribution.prob_dist

@@ -88,6 +88,8 @@ int check_utility(bopl_handle* h, int util_kind, int Lt, int p) {
     if (p != h->m) return fail(h, BOPL_ERR_INVALID, "linear/quadratic utility needs p == m parameters per sample");
   } else if (util_kind == BOPL_UTIL_EXPONENTIAL) {
     if (p != 1) return fail(h, BOPL_ERR_INVALID, "exponential utility needs p == 1");
+  } else if (util_kind == BOPL_UTIL_CONSTRAINED) {
+    if (p != h->m - 1 || h->m < 2) return fail(h, BOPL_ERR_INVALID, "constrained utility needs m >= 2 and p == m - 1 thresholds");
   } else {
     return fail(h, BOPL_ERR_INVALID, "unknown utility kind (no CPU fallback for arbitrary callables)");
   }
@@ -369,6 +371,7 @@ int bopl_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, co
   BOPL_NEED_MODEL(h);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
+  if (util_kind == BOPL_UTIL_CONSTRAINED) return fail(h, BOPL_ERR_INVALID, "the constrained utility has no MC kernel: use bopl_uei_constrained");
   if (N < 0 || nw <= 0) return fail(h, BOPL_ERR_INVALID, "bad N / nw");
   if (N && (!mean || !var || !Z || !theta || !wts || !best || !acq)) return fail(h, BOPL_ERR_INVALID, "null buffer");
   return launch_uei_mc(h, mean, var, N, Z, nw, util_kind, theta, Lt, p, wts, best, scale, accumulate, acq,
@@ -430,6 +433,30 @@ int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta
     if (dacq && (rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
     if ((rc = launch_uei_affine(h, h->mean_s, h->var_s, dacq ? h->dmean_s : nullptr, dacq ? h->dvar_s : nullptr, N, theta,
                                 Lt, wts, best + (size_t)hh * Lt, scale, hh > 0, acq, dacq, st)))
+      return rc;
+  }
+  return BOPL_OK;
+}
+
+int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
+                         const double* best, int nH, double* acq, double* dacq, void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (N < 0 || Lt <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / Lt / nH");
+  if (h->m < 2) return fail(h, BOPL_ERR_INVALID, "constrained EI needs at least one constraint attribute (m >= 2)");
+  if (N == 0) return BOPL_OK;
+  if (!Xc || !theta || !wts || !best || !acq) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (dacq && !h->has_winv) return fail(h, BOPL_ERR_STATE, "gradients need Winv (bopl_set_model was given NULL)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
+  if (dacq && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
+  const double scale = 1.0 / (double)nH;
+  for (int hh = 0; hh < nH; ++hh) {
+    if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
+    if (dacq && (rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
+    if ((rc = launch_uei_constrained(h, h->mean_s, h->var_s, dacq ? h->dmean_s : nullptr, dacq ? h->dvar_s : nullptr, N,
+                                     theta, Lt, wts, best + (size_t)hh * Lt, scale, hh > 0, acq, dacq, st)))
       return rc;
   }
   return BOPL_OK;

@@ -115,6 +115,9 @@ int launch_uei_mc_grad(bopl_handle* h, const double* mean, const double* var, co
 int launch_uei_affine(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
                       int N, const double* theta, int Lt, const double* wts, const double* best, double scale,
                       int accumulate, double* acq, double* dacq, cudaStream_t st);
+int launch_uei_constrained(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
+                           int N, const double* theta, int Lt, const double* wts, const double* best, double scale,
+                           int accumulate, double* acq, double* dacq, cudaStream_t st);
 int launch_topk(bopl_handle* h, const double* acq, int N, int k, long long index_offset, double* val, long long* idx,
                 cudaStream_t st);
 

@@ -1,7 +1,7 @@
 // gp_kernels.cu — the non-TRSM GP kernels of the hot path:
 //   kstar_kernel            K(Xc, X) (and g = dK/dr / r) materialised, for bopl_cross_cov and the gradient path
 //   posterior_mean_kernel   mu = K(Xc, X) alpha + ymean without the triangular solve
-//   beta_gemv / beta_gemm   beta = -2 K(Xc, X) Winv                       (GPy/core/gp.py:474)
+//   beta_gemm_kernel        beta = -2 K(Xc, X) Winv                       (GPy/core/gp.py:474)
 //   grad_contract_kernel    d mu / dx and d var / dx                      (GPy/kern/src/stationary.py:312-322)
 // Reference: GPy/kern/src/stationary.py:104-171,227-254,312-342; GPy/core/gp.py:380-400,438-490;
 // inference/latent_function_inference/posterior.py:299-305.
@@ -112,33 +112,9 @@ __global__ void __launch_bounds__(PM_TC* PM_RG) posterior_mean_kernel(MeanParams
 }
 
 // --------------------------------------------------------------------------------------------- beta = -2 K* Winv
-// Small batches (the L-BFGS inner loop calls with N = 1): one warp per training row i, Winv is symmetric so
-// beta[c][i] = -2 * dot(Winv[i, :], K*[c, :]) reads Winv rows coalesced.  Up to 4 candidates per pass.
-constexpr int GV_MAXC = 4;
-__global__ void __launch_bounds__(256) beta_gemv_kernel(const double* __restrict__ Winv, const double* __restrict__ K, int nc,
-                                                         int n, double* __restrict__ B) {
-  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const double* w = Winv + (size_t)warp * n;
-  double acc[GV_MAXC];
-#pragma unroll
-  for (int c = 0; c < GV_MAXC; ++c) acc[c] = 0.0;
-  for (int k = lane; k < n; k += 32) {
-    double wv = w[k];
-#pragma unroll
-    for (int c = 0; c < GV_MAXC; ++c)
-      if (c < nc) acc[c] = fma(K[(size_t)c * n + k], wv, acc[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < GV_MAXC; ++c) {
-    double v = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && c < nc) B[(size_t)c * n + warp] = -2.0 * v;
-  }
-}
-
-// Larger batches: B[Nc x n] = -2 * K[Nc x n] * Winv[n x n] on the FP64 tensor pipe (DMMA.8x8x4).
+// B[Nc x n] = -2 * K[Nc x n] * Winv[n x n] on the FP64 tensor pipe (DMMA.8x8x4), for every batch size: an output
+// element's accumulation order does not depend on the other rows of the batch, so a candidate's gradient is bit-identical
+// whether it is evaluated alone (the L-BFGS call shape) or inside a batch (the lock-step multi-start driver relies on it).
 // CTA tile 64 (cands) x 64 (cols), k-step 16, 4 warps (2 x 2), warp tile 32 x 32 = 16 accumulators.
 constexpr int GM_BM = 64, GM_BN = 64, GM_BK = 16, GM_NT = 128;
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -309,14 +285,9 @@ int launch_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, dou
       kstar_kernel<true><<<gridk, KS_NT, 0, st>>>(gp, xc, nc, d, n, h->pad, Kb, Gb);
       BOPL_LAUNCH_CHECK(h, "kstar_kernel<G>");
       if (dvar) {
-        if (nc <= GV_MAXC) {
-          beta_gemv_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
-          BOPL_LAUNCH_CHECK(h, "beta_gemv_kernel");
-        } else {
-          dim3 gg((n + GM_BN - 1) / GM_BN, (nc + GM_BM - 1) / GM_BM);
-          beta_gemm_kernel<<<gg, GM_NT, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
-          BOPL_LAUNCH_CHECK(h, "beta_gemm_kernel");
-        }
+        dim3 gg((n + GM_BN - 1) / GM_BN, (nc + GM_BM - 1) / GM_BM);
+        beta_gemm_kernel<<<gg, GM_NT, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
+        BOPL_LAUNCH_CHECK(h, "beta_gemm_kernel");
       }
       grad_contract_kernel<<<nc, GC_NT, 0, st>>>(gp, h->X_dev, xc, d, n, h->pad, Gb, dvar ? Bb : nullptr,
                                                  dmean ? dmean + ((size_t)j * N + s) * d : nullptr,

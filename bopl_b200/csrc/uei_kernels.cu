@@ -39,7 +39,13 @@ __device__ __forceinline__ double utility_value(const double* a, const double* t
     }
     return u;
   }
-  if (KIND == BOPL_UTIL_LINEAR) {
+  if (KIND == BOPL_UTIL_CONSTRAINED) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 1; j < MAX_M; ++j)
+      if (j < m) ok = ok && (th[j - 1] < a[j]);
+    return ok ? a[0] : -INFINITY;
+  } else if (KIND == BOPL_UTIL_LINEAR) {
 #pragma unroll
     for (int j = 0; j < MAX_M; ++j)
       if (j < m) u = fma(th[j], a[j], u);
@@ -321,6 +327,91 @@ __global__ void __launch_bounds__(128) uei_affine_kernel(McParams p) {
   }
 }
 
+// Closed-form constrained EI (uEI_constrained.py:49-73 value, :92-126,149-164 gradient).  One thread per candidate.
+// Per theta_l: EI0 = (mu0 - best) Phi0 + s0 phi0 (norm.pdf / norm.cdf, no floor), P = prod_j Phi_j, value = EI0 * P.
+// Gradient by the product rule (the reference's recursive aux_function_for_gradient unrolled):
+//   d = P (Phi0 dmu0 + phi0 (0.5/s0) dvar0) + EI0 sum_j phi_j Q_j (dmu_j / s_j - 0.5 (mu_j - theta_j) / var_j^1.5 dvar_j),
+//   Q_j = prod_{k != j} Phi_k.
+__global__ void __launch_bounds__(128) uei_constrained_kernel(McParams p) {
+  extern __shared__ double sm[];
+  const int pc = p.m - 1;
+  double* ths = sm;
+  double* ws = ths + p.Lt * pc;
+  double* bs = ws + p.Lt;
+  for (int i = threadIdx.x; i < p.Lt * pc; i += blockDim.x) ths[i] = p.theta[i];
+  for (int i = threadIdx.x; i < p.Lt; i += blockDim.x) {
+    ws[i] = p.wts[i];
+    bs[i] = p.best[i];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.N) return;
+  const int m = p.m, d = p.d;
+  const bool with_grad = p.dacq != nullptr;
+  const double inv_sqrt2pi = 0.39894228040143267794, inv_sqrt2 = 0.70710678118654752440;
+  double mu[MAX_M], sg[MAX_M], vr[MAX_M], cm[MAX_M], cv[MAX_M];
+#pragma unroll
+  for (int j = 0; j < MAX_M; ++j) {
+    cm[j] = cv[j] = 0.0;
+    if (j < m) {
+      mu[j] = p.mean[(size_t)j * p.N + c];
+      vr[j] = p.var[(size_t)j * p.N + c];
+      sg[j] = sqrt(vr[j]);
+    }
+  }
+  double acc = 0.0;
+  for (int l = 0; l < p.Lt; ++l) {
+    const double* th = ths + l * pc;
+    const double u0 = (mu[0] - bs[l]) / sg[0];
+    const double phi0 = exp(-0.5 * u0 * u0) * inv_sqrt2pi;
+    const double Phi0 = 0.5 * erfc(-u0 * inv_sqrt2);
+    const double ei0 = (mu[0] - bs[l]) * Phi0 + sg[0] * phi0;
+    double Phi[MAX_M], phi[MAX_M];
+    double P = 1.0;
+#pragma unroll
+    for (int j = 1; j < MAX_M; ++j)
+      if (j < m) {
+        const double u = (mu[j] - th[j - 1]) / sg[j];
+        Phi[j] = 0.5 * erfc(-u * inv_sqrt2);
+        phi[j] = exp(-0.5 * u * u) * inv_sqrt2pi;
+        P *= Phi[j];
+      }
+    acc = fma(ws[l], ei0 * P, acc);
+    if (with_grad) {
+      cm[0] = fma(ws[l] * P, Phi0, cm[0]);
+      cv[0] = fma(ws[l] * P, phi0 * 0.5 / sg[0], cv[0]);
+#pragma unroll
+      for (int j = 1; j < MAX_M; ++j)
+        if (j < m) {
+          double Q = 1.0;
+#pragma unroll
+          for (int k = 1; k < MAX_M; ++k)
+            if (k < m && k != j) Q *= Phi[k];
+          const double w = ws[l] * ei0 * phi[j] * Q;
+          cm[j] = fma(w, 1.0 / sg[j], cm[j]);
+          cv[j] = fma(w, -0.5 * (mu[j] - th[j - 1]) / (vr[j] * sg[j]), cv[j]);
+        }
+    }
+  }
+  double v = acc * p.scale;
+  p.acq[c] = p.accumulate ? p.acq[c] + v : v;
+  if (with_grad) {
+    for (int q = 0; q < d; ++q) {
+      double g = 0.0;
+#pragma unroll
+      for (int j = 0; j < MAX_M; ++j)
+        if (j < m) {
+          size_t o = ((size_t)j * p.N + c) * d + q;
+          g = fma(cm[j], p.dmean[o], g);
+          g = fma(cv[j], p.dvar[o], g);
+        }
+      g *= p.scale;
+      size_t o = (size_t)c * d + q;
+      p.dacq[o] = p.accumulate ? p.dacq[o] + g : g;
+    }
+  }
+}
+
 // best[h*Lt + l] = max_i U(F[h][:, i], theta_l);  F [H][m][n].  One block per (l, h).
 template <int KIND>
 __global__ void __launch_bounds__(256) incumbent_kernel(const double* __restrict__ F, int m, int n, const double* __restrict__ theta,
@@ -416,6 +507,21 @@ int launch_uei_affine(bopl_handle* h, const double* mean, const double* var, con
   return BOPL_OK;
 }
 
+int launch_uei_constrained(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
+                           int N, const double* theta, int Lt, const double* wts, const double* best, double scale,
+                           int accumulate, double* acq, double* dacq, cudaStream_t st) {
+  if (N <= 0) return BOPL_OK;
+  McParams mp{};
+  mp.mean = mean; mp.var = var; mp.dmean = dmean; mp.dvar = dvar; mp.theta = theta; mp.wts = wts; mp.best = best;
+  mp.acq = acq; mp.dacq = dacq;
+  mp.scale = scale; mp.N = N; mp.m = h->m; mp.d = h->d; mp.Lt = Lt; mp.p = h->m - 1; mp.accumulate = accumulate;
+  size_t smem = (size_t)(Lt * (h->m - 1) + 2 * Lt) * sizeof(double);
+  if (smem > 48 * 1024) return fail(h, BOPL_ERR_UNSUPPORTED, "uei_constrained: Lt*(m+1) exceeds 6144 doubles of shared staging");
+  uei_constrained_kernel<<<(N + 127) / 128, 128, smem, st>>>(mp);
+  BOPL_LAUNCH_CHECK(h, "uei_constrained_kernel");
+  return BOPL_OK;
+}
+
 int launch_incumbent(bopl_handle* h, const double* F, int util_kind, const double* theta, int Lt, int p, double* best,
                      cudaStream_t st) {
   dim3 grid(Lt, h->H);
@@ -423,6 +529,7 @@ int launch_incumbent(bopl_handle* h, const double* F, int util_kind, const doubl
     case BOPL_UTIL_LINEAR: incumbent_kernel<BOPL_UTIL_LINEAR><<<grid, 256, 0, st>>>(F, h->m, h->n, theta, Lt, p, best); break;
     case BOPL_UTIL_QUADRATIC: incumbent_kernel<BOPL_UTIL_QUADRATIC><<<grid, 256, 0, st>>>(F, h->m, h->n, theta, Lt, p, best); break;
     case BOPL_UTIL_EXPONENTIAL: incumbent_kernel<BOPL_UTIL_EXPONENTIAL><<<grid, 256, 0, st>>>(F, h->m, h->n, theta, Lt, p, best); break;
+    case BOPL_UTIL_CONSTRAINED: incumbent_kernel<BOPL_UTIL_CONSTRAINED><<<grid, 256, 0, st>>>(F, h->m, h->n, theta, Lt, p, best); break;
     default: return fail(h, BOPL_ERR_INVALID, "unknown utility kind");
   }
   BOPL_LAUNCH_CHECK(h, "incumbent_kernel");

@@ -182,6 +182,16 @@ class Engine(object):
                                              dacq.data_ptr() if with_grad else None, self._stream()))
         return acq, dacq
 
+    def uei_constrained_dev(self, Xc, theta, wts, best, nH, with_grad=False):
+        N = Xc.shape[0]
+        Lt = theta.shape[0]
+        acq = self.empty(N)
+        dacq = self.empty(N, self.d) if with_grad else None
+        self._check(self.lib.bopl_uei_constrained(self.h, Xc.data_ptr(), N, theta.data_ptr(), Lt, wts.data_ptr(),
+                                                  best.data_ptr(), nH, acq.data_ptr(),
+                                                  dacq.data_ptr() if with_grad else None, self._stream()))
+        return acq, dacq
+
     def topk_dev(self, acq, k, index_offset=0):
         torch = _torch()
         N = acq.shape[0]

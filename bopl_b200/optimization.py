@@ -1,0 +1,202 @@
+"""Caller of the hot path: the acquisition optimizer (SURVEY.md §8 a14 + §8f-1).
+
+Drop-in for `bopl/optimization_services/acquisition_optimizer.py:16-137` (AcquisitionOptimizer.optimize) and the pieces
+of `GPyOpt/optimization/optimizer.py` it uses (`OptLbfgs` :160-194, `apply_optimizer` :264-302) for continuous box
+domains:
+
+    candidates (random design, n_starting) -> batch acquisition scores -> n_anchor best -> L-BFGS-B from every anchor
+    -> best optimized point.
+
+Two things differ from the reference, neither changes a number:
+  * scoring + anchor selection is one fused GPU call when `f` is a bopl_b200 acquisition (anchor_points.py);
+  * the per-anchor L-BFGS-B runs (the reference does them one after the other, each calling `f_df` with ONE point,
+    acquisition_optimizer.py:112) run in LOCK-STEP: every anchor keeps its own, unmodified `scipy.optimize.fmin_l_bfgs_b`
+    (same `factr=1e6`, `maxiter`, bounds), on its own thread, and the `f_df` requests of all still-running anchors are
+    gathered into one batched GPU call.  A candidate's value and gradient do not depend on what else is in the batch
+    (the kernels are per-candidate deterministic), so every trajectory is bit-identical to the serial loop while the
+    number of GPU round trips drops by the number of anchors.  `batched=False` gives the reference's serial loop.
+"""
+import threading
+
+import numpy as np
+
+from .anchor_points import BoxSpace, ObjectiveAnchorPointsGenerator
+
+
+class ContextManager(object):
+    """acquisition_optimizer.py:287-331 reduced to a context-free continuous box."""
+
+    def __init__(self, space, context=None):
+        if context:
+            raise NotImplementedError("context variables are not on the accelerated path")
+        self.space = space
+        self.noncontext_bounds = space.get_bounds()
+
+    def _expand_vector(self, x):
+        return np.atleast_2d(x)
+
+
+class OptLbfgs(object):
+    """GPyOpt/optimization/optimizer.py:160-194."""
+
+    def __init__(self, bounds, maxiter=300):
+        self.bounds = bounds
+        self.maxiter = maxiter
+
+    def optimize(self, x0, f=None, df=None, f_df=None, verbose=False, maxfevals=1000):
+        import scipy.optimize
+        x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
+        if f_df is None and df is not None:
+            f_df = lambda x: (float(np.squeeze(f(x))), np.asarray(df(x)).reshape(-1))
+        if f_df is None:
+            res = scipy.optimize.fmin_l_bfgs_b(lambda x: float(np.squeeze(f(x))), x0=x0, bounds=self.bounds,
+                                               approx_grad=True, maxiter=self.maxiter)
+        else:
+            def fun(x):
+                fx, g = f_df(x)
+                return float(np.squeeze(fx)), np.asarray(g, dtype=np.float64).reshape(-1)
+            res = scipy.optimize.fmin_l_bfgs_b(fun, x0=x0, bounds=self.bounds, maxiter=self.maxiter, factr=1e6)
+        task = res[2]['task']
+        task = task.decode() if isinstance(task, bytes) else str(task)
+        if 'ABNORMAL' in task:                                   # optimizer.py:185-187: report x0, f(x0)
+            return np.atleast_2d(x0), (np.atleast_2d(f(np.atleast_2d(x0))) if f is not None else None)
+        return np.atleast_2d(res[0]), np.atleast_2d(res[1])
+
+
+def choose_optimizer(optimizer_name, bounds):
+    if optimizer_name != 'lbfgs':
+        raise NotImplementedError("only 'lbfgs' is supported (DIRECT / CMA are host-side options of the reference)")
+    return OptLbfgs(bounds)
+
+
+def _round_optimum(space, x):
+    """Continuous box: clip into the bounds (GPyOpt Design_space.round_optimum for continuous variables)."""
+    b = np.asarray(space.get_bounds(), dtype=np.float64)
+    return np.clip(np.atleast_2d(x), b[:, 0], b[:, 1])
+
+
+def apply_optimizer(optimizer, x0, f, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None):
+    """optimizer.py:264-302 without context / duplicate managers."""
+    x0 = np.atleast_2d(x0)
+    optimized_x, _ = optimizer.optimize(x0, f, df, f_df)
+    x = _round_optimum(space, optimized_x) if space is not None else np.atleast_2d(optimized_x)
+    return x, f(x)
+
+
+class LockstepBatcher(object):
+    """Gathers one `f_df(x)` request from every still-running worker into a single `f_df_batch(X)` call."""
+
+    def __init__(self, f_df_batch, n_workers):
+        self.f_df_batch = f_df_batch
+        self.active = n_workers
+        self.cv = threading.Condition()
+        self.pending = {}
+        self.results = {}
+        self.batches = 0
+        self.error = None
+
+    def _flush(self):
+        ids = sorted(self.pending)
+        X = np.stack([self.pending[i] for i in ids])
+        try:
+            fx, g = self.f_df_batch(X)
+            fx = np.asarray(fx, dtype=np.float64).reshape(len(ids))
+            g = np.asarray(g, dtype=np.float64).reshape(len(ids), -1)
+            for k, i in enumerate(ids):
+                self.results[i] = (float(fx[k]), g[k].copy())
+        except Exception as e:                                   # propagate to every waiting worker
+            self.error = e
+            for i in ids:
+                self.results[i] = None
+        self.batches += 1
+        self.pending.clear()
+        self.cv.notify_all()
+
+    def call(self, wid, x):
+        with self.cv:
+            self.pending[wid] = np.array(x, dtype=np.float64).reshape(-1)
+            if len(self.pending) == self.active:
+                self._flush()
+            else:
+                while wid not in self.results:
+                    self.cv.wait()
+            out = self.results.pop(wid)
+            if out is None:
+                raise self.error
+            return out
+
+    def done(self, wid):
+        with self.cv:
+            self.active -= 1
+            if self.pending and len(self.pending) == self.active:
+                self._flush()
+
+
+def lockstep_lbfgs(anchors, f_df_batch, bounds, maxiter=300):
+    """Run one unmodified scipy L-BFGS-B per anchor, in lock-step.  Returns (list of x_opt (1,d) or None-flag, batches)."""
+    n = len(anchors)
+    batcher = LockstepBatcher(f_df_batch, n)
+    out = [None] * n
+    errors = []
+
+    def work(i):
+        try:
+            opt = OptLbfgs(bounds, maxiter)
+            out[i] = opt.optimize(anchors[i], f_df=lambda x: batcher.call(i, x))
+        except Exception as e:
+            errors.append(e)
+        finally:
+            batcher.done(i)
+
+    threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out, batcher.batches
+
+
+class AcquisitionOptimizer(object):
+    """Same constructor surface as the reference (acquisition_optimizer.py:26); `optimize(f, df, f_df)` -> (x_min, fx_min)."""
+
+    def __init__(self, space, model=None, utility=None, expectation_utility=None, optimizer='lbfgs', inner_optimizer='lbfgs',
+                 parallel=False, n_starting=400, n_anchor=20, include_baseline_points=False, batched=True, **kwargs):
+        if include_baseline_points:
+            raise NotImplementedError("include_baseline_points (per-theta marginal argmax search, "
+                                      "acquisition_optimizer.py:87-100,139-249) is not on the accelerated path yet")
+        self.space = space if hasattr(space, "get_bounds") else BoxSpace(space)
+        self.model = model
+        self.utility = utility
+        self.expectation_utility = expectation_utility
+        self.optimizer_name = optimizer
+        self.inner_optimizer_name = inner_optimizer
+        self.parallel = parallel
+        self.n_starting = n_starting
+        self.n_anchor = n_anchor
+        self.include_baseline_points = include_baseline_points
+        self.batched = batched
+        self.kwargs = kwargs
+        self.context_manager = ContextManager(self.space)
+        self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
+        self.last_stats = {}
+
+    def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
+        self.f, self.df, self.f_df = f, df, f_df
+        self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
+        gen = ObjectiveAnchorPointsGenerator(self.space, "random", f, self.n_starting)
+        anchor_points, anchor_points_values = gen.get(num_anchor=self.n_anchor, duplicate_manager=duplicate_manager,
+                                                      context_manager=self.context_manager, get_scores=True)
+        if f_df is not None and self.batched and len(anchor_points) > 1:
+            results, batches = lockstep_lbfgs(list(anchor_points), f_df, self.optimizer.bounds, self.optimizer.maxiter)
+            X = np.vstack([_round_optimum(self.space, r[0]) for r in results])
+            fX = np.asarray(f(X), dtype=np.float64).reshape(len(X))          # apply_optimizer's closing f(x), batched
+            optimized_points = [(X[i:i + 1], np.atleast_2d(fX[i])) for i in range(len(X))]
+            self.last_stats = {"anchors": len(anchor_points), "f_df_batches": batches}
+        else:
+            optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, space=self.space)
+                                for a in anchor_points]
+            self.last_stats = {"anchors": len(anchor_points), "f_df_batches": None}
+        x_min, fx_min = min(optimized_points, key=lambda t: float(np.squeeze(t[1])))
+        return x_min, np.squeeze(fx_min)

@@ -107,6 +107,8 @@ def make_problem(name="S", n=None, N=None, n_w=None, L=None, H=1, kind="Mat52", 
             prob = np.ones(L) / L
     elif utility == "exponential":
         theta = (0.1 + 0.4 * r5.uniform(size=L)).reshape(L, 1)
+    elif utility == "constrained":       # attribute 0 = objective, attributes 1.. must exceed theta (test_portfolio2.py:64-79)
+        theta = Y[1:].mean(axis=1) - 0.5 * Y[1:].std(axis=1) * np.abs(r5.normal(size=(L, m - 1)))
     else:
         raise ValueError(utility)
     return dict(name=name, d=d, m=m, n=n, N=N, H=H, X=X, Y=Y, lo=lo, hi=hi, kinds=[kind] * m,

@@ -3,13 +3,14 @@
 
 In the reference a utility is an arbitrary Python callable; a CUDA kernel needs to know which closed form it is.
 `Utility(..., kind=...)` accepts 'linear' / 'quadratic' / 'exponential' (the callables of the named experiment
-configs: experiments/test_dtlz1a_linear.py:51-55, test_dtlz2a_quad.py:51-57, test_vlmop3_exp.py:41-52).  With
-`kind=None` the callable is probed against the three forms on random points (`infer_kind`); anything else raises —
+configs: experiments/test_dtlz1a_linear.py:51-55, test_dtlz2a_quad.py:51-57, test_vlmop3_exp.py:41-52) and 'constrained'
+(objective with threshold constraints, experiments/test_portfolio2.py:64-79, used by uEI_constrained).  With
+`kind=None` the callable is probed against the closed forms on random points (`infer_kind`); anything else raises —
 there is no CPU fallback for arbitrary callables.
 """
 import numpy as np
 
-UTILITY_KINDS = ("linear", "quadratic", "exponential")
+UTILITY_KINDS = ("linear", "quadratic", "exponential", "constrained")
 
 
 def preference_encoder(a, b):
@@ -32,6 +33,8 @@ def closed_form(kind, y, theta, m):
         return float(-np.sum(np.square(y - th)))
     if kind == "exponential":
         return float(np.sum(1.0 - np.exp(-th[0] * y)) / th[0] / m)
+    if kind == "constrained":
+        return float(y[0]) if np.all(th < y[1:]) else -np.inf
     raise ValueError(kind)
 
 
@@ -39,14 +42,13 @@ def infer_kind(func, m, theta, n_probe=6, rtol=1e-10, seed=12345):
     """Identify `func` as one of the three closed forms by probing it at random y with the given theta."""
     rs = np.random.RandomState(seed)
     th = np.asarray(theta, dtype=np.float64).reshape(-1)
-    if m == 1 and th.size == 1:
-        cands = list(UTILITY_KINDS)
-    elif th.size == m:
-        cands = ["linear", "quadratic"]
-    elif th.size == 1:
-        cands = ["exponential"]
-    else:
-        cands = []
+    cands = []
+    if th.size == m:
+        cands += ["linear", "quadratic"]
+    if th.size == 1:
+        cands += ["exponential"]
+    if m >= 2 and th.size == m - 1:
+        cands += ["constrained"]
     ys = rs.normal(size=(n_probe, m))
     for kind in cands:
         ok = True
@@ -57,6 +59,8 @@ def infer_kind(func, m, theta, n_probe=6, rtol=1e-10, seed=12345):
                 ok = False
                 break
             want = closed_form(kind, y, th, m)
+            if np.isinf(want) and got == want:
+                continue
             if not np.isfinite(got) or abs(got - want) > rtol * max(1.0, abs(want)):
                 ok = False
                 break

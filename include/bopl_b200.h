@@ -41,7 +41,10 @@ enum bopl_kernel_kind { BOPL_KERN_MAT52 = 0, BOPL_KERN_RBF = 1, BOPL_KERN_MAT32 
  * linear      U = theta . y                       experiments/test_dtlz1a_linear.py:51-55   (p = m)
  * quadratic   U = -sum_j (y_j - theta_j)^2        experiments/test_dtlz2a_quad.py:51-57     (p = m)
  * exponential U = (1/m) sum_j (1-exp(-theta y_j))/theta   experiments/test_vlmop3_exp.py:41-52 (p = 1) */
-enum bopl_utility_kind { BOPL_UTIL_LINEAR = 0, BOPL_UTIL_QUADRATIC = 1, BOPL_UTIL_EXPONENTIAL = 2 };
+enum bopl_utility_kind { BOPL_UTIL_LINEAR = 0, BOPL_UTIL_QUADRATIC = 1, BOPL_UTIL_EXPONENTIAL = 2,
+                         /* y_0 if theta_{j-1} < y_j for every j >= 1, else -inf: experiments/test_portfolio2.py:64-79 (p = m-1);
+                          * accepted by bopl_incumbent only (uEI_constrained has its own closed-form entry point) */
+                         BOPL_UTIL_CONSTRAINED = 3 };
 
 /* bopl_posterior flags */
 #define BOPL_VAR_INCLUDE_NOISE 1 /* add the Gaussian likelihood variance: GPy/core/gp.py:416-417, likelihoods/gaussian.py:110-111 */
@@ -130,6 +133,13 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
  * gradient path: uEI_affine._marginal_acq_with_gradient, uEI_affine.py:91-116 (no floor).                       */
 int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
                     const double* best, int nH, double* acq, double* dacq, void* stream);
+
+/* Closed-form constrained EI: attribute 0 is the objective, attributes 1..m-1 are constraints y_j > theta_{l,j-1}:
+ *   acq = (1/nH) sum_h sum_l wts[l] * EI(mean_0, sigma_0; best[h,l]) * prod_{j>=1} Phi((mean_j - theta_{l,j-1}) / sigma_j)
+ * theta [Lt*(m-1)], best [nH*Lt]; acq [N], dacq [N*d] or NULL.  Replaces uEI_constrained._compute_acq /
+ * _compute_acq_withGradients: sampling_policies/acquisition_functions/uEI_constrained.py:36-126,149-164. */
+int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
+                         const double* best, int nH, double* acq, double* dacq, void* stream);
 
 /* ---- anchor selection ---------------------------------------------------------------------------------------
  * The k largest acq values of this shard, ties -> lowest index; idx are GLOBAL indices (local + index_offset).

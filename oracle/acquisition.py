@@ -10,7 +10,7 @@ import numpy as np
 from scipy.special import erfc
 from scipy.stats import norm
 
-UTILITY_KINDS = ("linear", "quadratic", "exponential")
+UTILITY_KINDS = ("linear", "quadratic", "exponential", "constrained")
 
 
 # ----------------------------------------------------------------------------- θ aggregation
@@ -265,6 +265,84 @@ def uei_affine_marginal_with_gradient_loop(model, thetas, X, n_h):
                 dmu_dX = np.matmul(thetas[l], dmean_dX[:, i, :])
                 dsigma_dX = 0.5 * np.matmul(np.square(thetas[l]), dvar_dX[:, i, :]) / sigma
                 marginal_d[i, :, l] += dmu_dX * Phi + phi * dsigma_dX
+    return marginal / n_h, marginal_d / n_h
+
+
+# ----------------------------------------------------------------------------- uEI_constrained (closed form)
+def constrained_best_so_far(model, func, thetas):
+    """uEI_constrained._marginal_max_feasible_val_so_far, uEI_constrained.py:136-146 (model's CURRENT hyper-sample)."""
+    F = model.posterior_mean_at_evaluated_points()
+    return np.array([np.max(func(F, thetas[l])) for l in range(len(thetas))])
+
+
+def uei_constrained_marginal_loop(model, func, thetas, X, n_h):
+    """uEI_constrained._marginal_acq, uEI_constrained.py:49-73."""
+    X = np.atleast_2d(X)
+    L = len(thetas)
+    marginal = np.zeros((X.shape[0], L))
+    best = constrained_best_so_far(model, func, thetas)
+    for h in range(n_h):
+        model.set_hyperparameters(h)
+        meanX, varX = model.predict(X)
+        sigmaX = np.sqrt(varX)
+        for l in range(L):
+            for i in range(X.shape[0]):
+                mu, sigma = meanX[0, i], sigmaX[0, i]
+                phi = norm.pdf((mu - best[l]) / sigma)
+                Phi = norm.cdf((mu - best[l]) / sigma)
+                val = (mu - best[l]) * Phi + sigma * phi
+                for j in range(1, meanX.shape[0]):
+                    val *= norm.cdf((meanX[j, i] - thetas[l][j - 1]) / sigmaX[j, i])
+                marginal[i, l] += val
+    return marginal / n_h
+
+
+def _aux_function_for_gradient(mean, var, mean_gradient, var_gradient, theta):
+    """uEI_constrained.py:149-164 (recursive product rule over the feasibility factors)."""
+    j = len(mean)
+    mu = mean[j - 1]
+    sigma = np.sqrt(var[j - 1])
+    output = norm.pdf((mu - theta[j - 1]) / sigma) * ((mean_gradient[j - 1, :] / sigma)
+                                                      - (0.5 * (mu - theta[j - 1]) / np.power(var[j - 1], 1.5)) * var_gradient[j - 1, :])
+    if j == 1:
+        return output
+    Phi_aux = norm.cdf((mu - theta[j - 1]) / sigma)
+    for k in range(j - 1):
+        output = output * norm.cdf((mean[k] - theta[k]) / np.sqrt(var[k]))
+    output = output + Phi_aux * _aux_function_for_gradient(mean[:j - 1], var[:j - 1], mean_gradient[:j - 1, :],
+                                                           var_gradient[:j - 1, :], theta[:j - 1])
+    return output
+
+
+def uei_constrained_marginal_with_gradient_loop(model, func, thetas, X, n_h):
+    """uEI_constrained._marginal_acq_with_gradient, uEI_constrained.py:92-126."""
+    X = np.atleast_2d(X)
+    L = len(thetas)
+    marginal = np.zeros((X.shape[0], L))
+    marginal_d = np.zeros((X.shape[0], X.shape[1], L))
+    best = constrained_best_so_far(model, func, thetas)
+    for h in range(n_h):
+        model.set_hyperparameters(h)
+        meanX, varX = model.predict(X)
+        sigmaX = np.sqrt(varX)
+        dmean_dX = model.posterior_mean_gradient(X)
+        dvar_dX = model.posterior_variance_gradient(X)
+        for l in range(L):
+            for i in range(X.shape[0]):
+                mu, sigma = meanX[0, i], sigmaX[0, i]
+                phi = norm.pdf((mu - best[l]) / sigma)
+                Phi = norm.cdf((mu - best[l]) / sigma)
+                val = (mu - best[l]) * Phi + sigma * phi
+                val_aux = np.copy(val)
+                gradient = dmean_dX[0, i, :] * Phi + phi * (0.5 / sigma) * dvar_dX[0, i, :]
+                for j in range(1, meanX.shape[0]):
+                    Phi = norm.cdf((meanX[j, i] - thetas[l][j - 1]) / sigmaX[j, i])
+                    val *= Phi
+                    gradient = gradient * Phi
+                gradient = gradient + val_aux * _aux_function_for_gradient(meanX[1:, i], varX[1:, i], dmean_dX[1:, i, :],
+                                                                           dvar_dX[1:, i, :], thetas[l])
+                marginal[i, l] += val
+                marginal_d[i, :, l] += gradient
     return marginal / n_h, marginal_d / n_h
 
 

@@ -43,6 +43,16 @@ def make_exponential(m):
     return exponential_func, exponential_gradient
 
 
+def constrained_func(y, parameter):
+    """experiments/test_portfolio2.py:64-79 generalised to m-1 constraints: y_0 if parameter_j < y_{j+1} for all j."""
+    y_aux = np.squeeze(y)
+    par = np.atleast_1d(np.squeeze(parameter))
+    if y_aux.ndim > 1:
+        ok = np.all(par[:, None] < y_aux[1:], axis=0)
+        return np.where(ok, y_aux[0], -np.inf)
+    return y_aux[0] if np.all(par < y_aux[1:]) else -np.inf
+
+
 def get(kind, m):
     """(func, gradient) for kind in {'linear','quadratic','exponential'}."""
     if kind == "linear":
@@ -51,4 +61,6 @@ def get(kind, m):
         return quadratic_func, quadratic_gradient
     if kind == "exponential":
         return make_exponential(m)
+    if kind == "constrained":
+        return constrained_func, None
     raise ValueError(kind)

@@ -209,6 +209,8 @@ def build_reference():
     _load("aux_software.GPyOpt.acquisitions.base", os.path.join(GPYOPT, "acquisitions/base.py"))
     R.uEI = _load("ref_uEI", os.path.join(REF, "bopl/sampling_policies/acquisition_functions/uEI.py")).uEI
     R.uEI_affine = _load("ref_uEI_affine", os.path.join(REF, "bopl/sampling_policies/acquisition_functions/uEI_affine.py")).uEI_affine
+    R.uEI_constrained = _load("ref_uEI_constrained",
+                              os.path.join(REF, "bopl/sampling_policies/acquisition_functions/uEI_constrained.py")).uEI_constrained
 
     # --- utility callables of the experiment scripts
     def exp_utils(script, m):
@@ -311,5 +313,44 @@ def main():
             print("wrote uEI_affine_%s.npz" % name)
 
 
+CONSTRAINED_CASES = [  # (problem name, kwargs): m = 2 uses the reference's own callable of experiments/test_portfolio2.py
+    ("dtlz1a_linear", dict(N=40, n=30, L=5, H=2, utility="constrained")),       # m = 2: one constraint
+    ("vlmop3_exp", dict(N=40, n=30, L=5, H=1, utility="constrained")),          # m = 3: two constraints
+]
+
+
+def main_constrained():
+    from bopl_b200.synthetic import make_problem
+    from oracle import utilities
+    R = build_reference()
+    for name, kw in CONSTRAINED_CASES:
+        p = make_problem(name, **kw)
+        model = reference_model(R, p)
+        if p["m"] == 2:      # the reference's own utility callable (one scalar threshold)
+            mods = harvest_functions(os.path.join(REF, "experiments", "test_portfolio2.py"), ["utility_func"])
+            scope = dict(np=np)
+            np.infty = np.inf                                    # numpy 2 dropped the alias the script uses
+            exec(compile(mods["utility_func"], "test_portfolio2.py", "exec"), scope)
+            func = scope["utility_func"]
+        else:                # the script's callable handles one constraint only; same rule for m-1 thresholds
+            func = utilities.constrained_func
+        theta = p["theta"]
+        dist = R.UtilityDistribution(prior_sample_generator=lambda n_s, seed=None: theta[:n_s], utility_func=func,
+                                     use_full_support=False)
+        util = R.Utility(func=func, parameter_distribution=dist)
+        acq = R.uEI_constrained(model, None, optimizer=None, utility=util)
+        acq.utility_parameter_samples = theta
+        acq.number_of_gp_hyps_samples = p["H"]
+        X = p["Xc"]
+        out = dict(name=name, acq="uEI_constrained", N=kw["N"], n=kw["n"], L=kw["L"], H=kw["H"], Xc=X, theta=theta)
+        model.set_hyperparameters(0)
+        out["acq_value"] = acq._compute_acq(X)
+        model.set_hyperparameters(0)
+        out["acq_grad_f"], out["acq_grad_df"] = acq._compute_acq_withGradients(X)
+        np.savez(os.path.join(HERE, "uEIc_%s.npz" % name), **out)
+        print("wrote uEIc_%s.npz  acq range [%.3e, %.3e]" % (name, out["acq_value"].min(), out["acq_value"].max()))
+
+
 if __name__ == "__main__":
     main()
+    main_constrained()

@@ -380,3 +380,54 @@ def test_cuda_path_against_reference_generated_golden(fname):
         f, df = acq._compute_acq_withGradients(X)
         check_close(f, g["acq_grad_f"], fname + " affine f")
         check_close(df, g["acq_grad_df"], fname + " affine df", rtol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------- optimizer (caller)
+def test_acquisition_optimizer_batched_equals_serial_on_gpu():
+    """AcquisitionOptimizer.optimize through the GPU acquisition: lock-step batched L-BFGS == the reference's serial loop,
+    and the result is at least as good as the best anchor."""
+    from bopl_b200.optimization import AcquisitionOptimizer
+    p = make_problem("dtlz2a_quad", N=400)
+    gm = gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    out = []
+    for batched in (True, False):
+        np.random.seed(7)
+        opt = AcquisitionOptimizer(acq.space, model=gm, utility=acq.utility, n_starting=400, n_anchor=6, batched=batched)
+        acq.optimizer = opt
+        x, fx = acq.optimize()
+        out.append((x, float(fx), opt.last_stats))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    np.random.seed(7)
+    from bopl_b200.anchor_points import samples_multidimensional_uniform
+    X0 = samples_multidimensional_uniform(acq.space.get_bounds(), 400)
+    assert out[0][1] <= float(acq.acquisition_function(X0).min()) + 1e-12
+    assert out[0][2]["f_df_batches"] is not None
+
+
+@pytest.mark.parametrize("fname", _golden("uEIc_"))
+def test_uei_constrained_against_reference_generated_golden(fname):
+    """uEI_constrained (closed-form EI x feasibility probabilities): CUDA path vs the reference's own code and vs the oracle."""
+    import os
+    from bopl_b200.acquisition import uEI_constrained
+    from oracle import utilities
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname), allow_pickle=False)
+    name, H = str(g["name"]), int(g["H"])
+    p = make_problem(name, N=int(g["N"]), n=int(g["n"]), L=int(g["L"]), H=H, utility="constrained")
+    gm = gpu_model(p)
+    acq = gpu_acquisition(p, gm, cls=uEI_constrained)
+    gm.set_hyperparameters(0)
+    check_close(acq._compute_acq(p["Xc"]), g["acq_value"], fname + " value")
+    gm.set_hyperparameters(0)
+    f, df = acq._compute_acq_withGradients(p["Xc"])
+    check_close(f, g["acq_grad_f"], fname + " f")
+    check_close(df, g["acq_grad_df"], fname + " df", rtol=1e-7)
+    assert np.argmax(f) == np.argmax(g["acq_grad_f"])
+    # a larger batch against the oracle's loop-faithful restatement
+    p2 = make_problem(name, N=150, n=45, L=6, H=H, utility="constrained")
+    om, gm2 = oracle_model(p2), gpu_model(p2)
+    func, _ = utilities.get("constrained", p2["m"])
+    acq2 = gpu_acquisition(p2, gm2, cls=uEI_constrained)
+    want = oacq.aggregate(oacq.uei_constrained_marginal_loop(om, func, p2["theta"], p2["Xc"], H), False, None)
+    gm2.set_hyperparameters(0)
+    check_close(acq2._compute_acq(p2["Xc"]), want, fname + " value N=150")

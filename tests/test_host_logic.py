@@ -51,14 +51,15 @@ def test_product_never_imports_the_oracle():
 
 
 @pytest.mark.parametrize("kind,m,theta", [("linear", 3, [0.2, 0.3, 0.5]), ("quadratic", 4, [0.1, -0.4, 0.3, 1.0]),
-                                           ("exponential", 3, [0.25])])
+                                           ("exponential", 3, [0.25]), ("constrained", 2, [-0.1]),
+                                           ("constrained", 4, [-0.2, 0.1, -0.5])])
 def test_utility_kind_inference(kind, m, theta):
     func, grad = utilities.get(kind, m)
     assert infer_kind(func, m, np.array(theta)) == kind
     u = Utility(func=func, gradient=grad, parameter_distribution=None)
     assert u.resolve_kind(m, np.array(theta)) == kind
     y = np.random.RandomState(0).normal(size=m)
-    assert np.allclose(u.eval_func(y, np.array(theta)), func(y, np.array(theta)))
+    assert np.array_equal(np.asarray(u.eval_func(y, np.array(theta))), np.asarray(func(y, np.array(theta))))
 
 
 def test_utility_kind_inference_rejects_unknown_callable():
@@ -177,3 +178,48 @@ def test_host_fit_matches_oracle_fit():
         assert np.allclose(L, np.tril(g.L), rtol=1e-12, atol=1e-14)
         assert np.allclose(alpha, g.alpha[:, 0], rtol=1e-9) and ymean == g.ymean
         assert np.allclose(Winv, g.Winv, rtol=1e-9, atol=1e-9 * np.abs(g.Winv).max())
+
+
+def test_lockstep_lbfgs_equals_serial_scipy():
+    """Every anchor's L-BFGS-B trajectory in the batched lock-step driver is the serial one (same f_df values in,
+    same iterates out), while the number of f_df round trips drops to the longest single run."""
+    from bopl_b200.optimization import OptLbfgs, lockstep_lbfgs
+    rs = np.random.RandomState(0)
+    A = rs.normal(size=(4, 4))
+    A = A @ A.T + np.eye(4)
+    calls = {"batch": 0, "points": 0}
+
+    def f_df_batch(X):
+        X = np.atleast_2d(X)
+        calls["batch"] += 1
+        calls["points"] += len(X)
+        fs, gs = [], []
+        for x in X:                       # row by row: a point's value must not depend on the batch it travels in
+            y = x - 0.3
+            Ay = A @ y
+            fs.append(0.5 * float(y @ Ay) + float(np.sum(np.cos(3 * x))))
+            gs.append(Ay - 3 * np.sin(3 * x))
+        return np.array(fs)[:, None], np.array(gs)
+
+    bounds = [(0.0, 1.0)] * 4
+    anchors = rs.uniform(size=(7, 4))
+    serial = [OptLbfgs(bounds).optimize(a, f_df=lambda x: tuple(v[0] for v in f_df_batch(x))) for a in anchors]
+    n_serial_calls = calls["points"]
+    calls.update(batch=0, points=0)
+    batched, nb = lockstep_lbfgs(list(anchors), f_df_batch, bounds)
+    for s, b in zip(serial, batched):
+        assert np.array_equal(s[0], b[0]) and np.array_equal(s[1], b[1])
+    assert calls["points"] == n_serial_calls and nb == calls["batch"] < n_serial_calls
+
+
+def test_acquisition_optimizer_host_path_returns_best_local_optimum():
+    from bopl_b200.optimization import AcquisitionOptimizer
+    f = lambda X: np.sum((np.atleast_2d(X) - 0.7) ** 2, axis=1, keepdims=True)
+    f_df = lambda X: (f(X), 2 * (np.atleast_2d(X) - 0.7))
+    np.random.seed(0)
+    for batched in (True, False):
+        opt = AcquisitionOptimizer(BoxSpace([(0, 1)] * 3), n_starting=50, n_anchor=5, batched=batched)
+        x, fx = opt.optimize(f=f, f_df=f_df)
+        assert x.shape == (1, 3) and np.allclose(x, 0.7, atol=1e-5) and fx < 1e-9
+    with pytest.raises(NotImplementedError):
+        AcquisitionOptimizer(BoxSpace([(0, 1)] * 3), include_baseline_points=True)

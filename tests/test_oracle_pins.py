@@ -179,6 +179,19 @@ def test_oracle_against_reference_generated_golden(fname):
     """Fixtures made by running the reference's own uEI.py / uEI_affine.py code (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, fname), allow_pickle=False)
     name, H = str(g["name"]), int(g["H"])
+    if str(g["acq"]) == "uEI_constrained":
+        p = make_problem(name, N=int(g["N"]), n=int(g["n"]), L=int(g["L"]), H=H, utility="constrained")
+        assert np.array_equal(p["Xc"], g["Xc"]) and np.array_equal(p["theta"], g["theta"])
+        om = oracle_model(p)
+        func, _ = utilities.get("constrained", p["m"])
+        om.set_hyperparameters(0)
+        marg = oacq.uei_constrained_marginal_loop(om, func, p["theta"], p["Xc"], H)
+        assert np.allclose(oacq.aggregate(marg, False, None), g["acq_value"], rtol=1e-11, atol=1e-13)
+        om.set_hyperparameters(0)
+        f, d = oacq.uei_constrained_marginal_with_gradient_loop(om, func, p["theta"], p["Xc"], H)
+        assert np.allclose(oacq.aggregate(f, False, None), g["acq_grad_f"], rtol=1e-11, atol=1e-13)
+        assert np.allclose(oacq.aggregate_gradient(d, False, None), g["acq_grad_df"], rtol=1e-9, atol=1e-12 * np.abs(g["acq_grad_df"]).max())
+        return
     p = make_problem(name, N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=H)
     assert np.array_equal(p["Xc"], g["Xc"]) and np.array_equal(p["Z"], g["Z"]) and np.array_equal(p["theta"], g["theta"])
     om = oracle_model(p)
