@@ -137,7 +137,8 @@ def run_gpu(args):
     N = w["N"]
     p = make_problem("S", n=w["n"], N=16, n_w=w["n_w"], L=w["L"])
     d, m = p["d"], p["m"]
-    state = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"], want_winv=False)
+    state = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"], want_winv=False,
+                                       want_linv=False)
     model = MultiOutputGP.from_state(state, device=local_rank)
     eng = model.engine
     theta = p["theta"]

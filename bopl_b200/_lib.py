@@ -82,7 +82,7 @@ def load():
     lib.bopl_device_sms.argtypes = [vp]
     lib.bopl_build_info.argtypes = []
     lib.bopl_build_info.restype = ctypes.c_char_p
-    lib.bopl_set_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.bopl_set_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.bopl_cross_cov.argtypes = [vp, dp, c_int, c_int, c_int, dp, vp]
     lib.bopl_posterior.argtypes = [vp, dp, c_int, c_int, dp, dp, c_int, vp]
     lib.bopl_posterior_mean.argtypes = [vp, dp, c_int, c_int, dp, vp]

@@ -38,6 +38,7 @@ void free_model(bopl_handle* h) {
   h->X_dev = nullptr;
   h->has_model = false;
   h->has_winv = false;
+  h->has_linv = false;
   h->F_valid = false;
 }
 
@@ -160,6 +161,7 @@ int bopl_create(bopl_handle** out, int device) {
   h->sms = prop.multiProcessorCount;
   if (const char* v = getenv("BOPL_TRSM_VARIANT")) h->trsm_variant = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
+  if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
@@ -179,7 +181,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -201,7 +203,7 @@ long long bopl_launch_count(const bopl_handle* h) { return h ? h->launches : 0; 
 
 int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
                    const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
-                   const double* L_h, const double* alpha_h, const double* Winv_h) {
+                   const double* L_h, const double* alpha_h, const double* Winv_h, const double* Linv_h) {
   BOPL_CHECK_HANDLE(h);
   if (n <= 0 || d <= 0 || m <= 0 || H <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, m, H must be positive");
   if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
@@ -275,6 +277,12 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       free_model(h);
       return rc;
     }
+    double* pLi = nullptr;
+    if (Linv_h && (rc = dev_upload(h, Linv_h + (size_t)g * n * n, (size_t)n * n, &pLi))) {
+      free_model(h);
+      return rc;
+    }
+    gp.Linv = pLi;
     gp.Lneg = pL;
     gp.Dinv = pD;
     gp.DinvFrag = pF;
@@ -295,6 +303,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   }
   h->gp_dev = gd;
   h->has_winv = Winv_h != nullptr;
+  h->has_linv = Linv_h != nullptr;
   h->has_model = true;
   h->F_valid = false;
   return BOPL_OK;

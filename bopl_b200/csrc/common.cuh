@@ -17,6 +17,7 @@ constexpr int TRSM_BK = 16;    // k-depth of one pipeline stage
 constexpr int MAX_D = 24;      // input dimensions the shared-memory staging is sized for
 constexpr int MAX_M = 16;      // attributes
 constexpr int MAX_TOPK = 256;
+constexpr int SMALL_N = 32;     // batches up to this size take the matrix-vector path (explicit inverse factor) when Linv is loaded
 
 // Device-side view of one GP (attribute j under hyper-sample h).  All pointers device memory owned by the handle.
 struct GpDev {
@@ -26,6 +27,7 @@ struct GpDev {
   const double* Xs;      // [n_pad*d] training inputs divided by the lengthscales, front-padded with zeros
   const double* alpha;   // [n_pad] woodbury vector, front-padded with zeros
   const double* Winv;    // [n*n] or nullptr
+  const double* Linv;    // [n*n] explicit inverse of the Cholesky factor (lower triangular, row-major) or nullptr
   const double* ell;     // [d]
   double variance, noise, ymean;
   int kind;
@@ -39,7 +41,9 @@ struct bopl_handle {
   int sms = 0;
   int n = 0, d = 0, m = 0, H = 0;
   int n_pad = 0, pad = 0;
-  bool has_model = false, has_winv = false;
+  bool has_model = false, has_winv = false, has_linv = false;
+  int small_path = 1;                  // BOPL_SMALL_PATH=0 forces the blocked TRSM kernel for every batch size
+  double* small_scratch = nullptr; size_t small_scratch_bytes = 0;
   std::string err;
   long long launches = 0;
   int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
@@ -97,6 +101,9 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st);
 void pack_dinv_fragments(const double* Dinv_block, double* out);
+bool use_small_path(const bopl_handle* h, int N);
+int launch_posterior_small(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
+                           cudaStream_t st);
 int launch_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, cudaStream_t st);
 int launch_posterior_mean_strided(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, long long out_stride,
                                   cudaStream_t st);

@@ -363,6 +363,7 @@ int launch_cfg(bopl_handle* h, TrsmParams& p, cudaStream_t st) {
 int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                           cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
+  if (use_small_path(h, N)) return launch_posterior_small(h, Xc, N, hsel, mean, var, flags, st);
   if (h->trsm_variant != 1 && h->trsm_variant != 2) return launch_posterior_trsm_t(h, Xc, N, hsel, mean, var, flags, st);
   TrsmParams p;
   p.gps = h->gp_dev;

@@ -16,10 +16,11 @@ class GPState(object):
     """Flat fp64 arrays of m attributes x H hyper-samples of exact GPs — what `bopl_set_model` consumes.
 
     kinds (m,H) of GPy kernel names; X (n,d); lengthscale (m,H,d); variance, noise, ymean (m,H);
-    L (m,H,n,n) lower Cholesky factors of K + (noise+1e-8) I, C order; alpha (m,H,n); Winv (m,H,n,n) or None.
+    L (m,H,n,n) lower Cholesky factors of K + (noise+1e-8) I, C order; alpha (m,H,n); Winv (m,H,n,n) or None;
+    Linv (m,H,n,n) = L^-1 (dtrtri) or None — enables the small-batch matrix-vector path.
     Field map from the reference's live objects: SURVEY.md §7.1-10."""
 
-    def __init__(self, kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv=None):
+    def __init__(self, kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv=None, Linv=None):
         self.X = np.ascontiguousarray(X, dtype=np.float64)
         self.n, self.d = self.X.shape
         self.variance = np.ascontiguousarray(variance, dtype=np.float64)
@@ -32,6 +33,8 @@ class GPState(object):
         self.alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(self.m, self.H, self.n)
         self.Winv = None if Winv is None else \
             np.ascontiguousarray(Winv, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
+        self.Linv = None if Linv is None else \
+            np.ascontiguousarray(Linv, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
 
 
 def _torch():
@@ -94,7 +97,8 @@ class Engine(object):
         self._check(self.lib.bopl_set_model(
             self.h, state.n, state.d, state.m, state.H, p(kinds), p(state.X), p(state.lengthscale), p(state.variance),
             p(state.noise), p(state.ymean), p(state.L), p(state.alpha),
-            p(state.Winv) if state.Winv is not None else None))
+            p(state.Winv) if state.Winv is not None else None,
+            p(state.Linv) if state.Linv is not None else None))
         self.state = state
         self.n, self.d, self.m, self.H = state.n, state.d, state.m, state.H
 

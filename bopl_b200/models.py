@@ -69,7 +69,15 @@ def fit_exact_gp(X, Y, kind, variance, lengthscale, noise, want_winv=True):
     return np.tril(L), alpha[:, 0], ymean, Winv
 
 
-def state_from_hyperparameters(X, Y, kinds, variance, lengthscale, noise, want_winv=True):
+def inverse_factor(L):
+    """L^-1 by LAPACK dtrtri (lower, non-unit) — the factor of the small-batch matrix-vector path."""
+    Linv, info = lapack.dtrtri(np.asfortranarray(L), lower=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("dtrtri failed (info=%d)" % info)
+    return np.tril(Linv)
+
+
+def state_from_hyperparameters(X, Y, kinds, variance, lengthscale, noise, want_winv=True, want_linv=True):
     """Build a GPState for m attributes x H hyper-samples.  Y: list / array of m vectors (n,) or (n,1)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     variance = np.asarray(variance, dtype=np.float64)
@@ -85,13 +93,16 @@ def state_from_hyperparameters(X, Y, kinds, variance, lengthscale, noise, want_w
     alpha = np.empty((m, H, n))
     ymean = np.empty((m, H))
     Winv = np.empty((m, H, n, n)) if want_winv else None
+    Linv = np.empty((m, H, n, n)) if want_linv else None
     for j in range(m):
         for h in range(H):
             Lj, aj, yj, Wj = fit_exact_gp(X, Y[j], str(kinds[j, h]), variance[j, h], lengthscale[j, h], noise[j, h], want_winv)
             L[j, h], alpha[j, h], ymean[j, h] = Lj, aj, yj
             if want_winv:
                 Winv[j, h] = Wj
-    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv)
+            if want_linv:
+                Linv[j, h] = inverse_factor(Lj)
+    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv)
 
 
 def state_from_reference_model(ref_model, want_winv=True):
@@ -122,7 +133,8 @@ def state_from_reference_model(ref_model, want_winv=True):
             alpha[j, h] = np.asarray(g.posterior.woodbury_vector, dtype=np.float64).reshape(-1)
             if want_winv:
                 Winv[j, h] = np.asarray(g.posterior.woodbury_inv, dtype=np.float64).reshape(n, n)
-    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv)
+    Linv = np.stack([np.stack([inverse_factor(L[j, h]) for h in range(H)]) for j in range(m)])
+    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv)
 
 
 # ------------------------------------------------------------------------------------------- the drop-in class

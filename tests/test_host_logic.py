@@ -161,7 +161,7 @@ def test_state_extractor_on_reference_shaped_objects():
                                  woodbury_inv=st.Winv[j, h])) for h in range(st.H)]
         outs.append(NS(model_instances=insts))
     st2 = state_from_reference_model(NS(output_dim=st.m, output=outs))
-    for f in ("X", "lengthscale", "variance", "noise", "ymean", "L", "alpha", "Winv"):
+    for f in ("X", "lengthscale", "variance", "noise", "ymean", "L", "alpha", "Winv", "Linv"):
         assert np.array_equal(getattr(st, f), getattr(st2, f)), f
     assert (st.kinds == st2.kinds).all()
 
