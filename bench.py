@@ -124,6 +124,10 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the GPU arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
@@ -261,7 +265,8 @@ def run_gpu(args):
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                    "sample": "%d of the %d candidates, one pass of the NumPy/SciPy (LAPACK dtrtrs) restatement, %.1f s"
                                              % (args.cpu_sample, N, t)}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -431,3 +431,29 @@ def test_uei_constrained_against_reference_generated_golden(fname):
     want = oacq.aggregate(oacq.uei_constrained_marginal_loop(om, func, p2["theta"], p2["Xc"], H), False, None)
     gm2.set_hyperparameters(0)
     check_close(acq2._compute_acq(p2["Xc"]), want, fname + " value N=150")
+
+
+# ------------------------------------------------------------------------------------------------- BASELINE.json full size
+def test_full_size_config_S_properties_and_subset_parity():
+    """Config S at BASELINE.json's full size (n=2000, m=3, d=10, N=2^20, n_w=64, L=32) through the reference-facing call.
+    Size-independent properties: scores are finite and >= 0; the anchors are the stable argsort of the scores; a
+    sub-batch scored on its own reproduces its slice bit for bit; a permuted sub-batch permutes the scores bit for bit.
+    Parity: the first 2048 candidates against the oracle, 1e-9 of scale, identical argmax."""
+    p = make_problem("S")
+    assert p["Xc"].shape == (2 ** 20, 10) and p["n"] == 2000
+    gm = gpu_model(p, gradients=False)
+    acq = gpu_acquisition(p, gm)
+    val, idx, a = acq.top_candidates(p["Xc"], 20, want_acq=True)
+    assert a.shape == (2 ** 20,) and np.all(np.isfinite(a)) and np.all(a >= 0.0)
+    want = np.argsort(-a, kind="stable")[:20]
+    assert np.array_equal(idx, want) and np.array_equal(val, a[want])
+    sl = slice(300000, 300000 + 70001)                       # ragged size, several tiles, > one small batch
+    assert np.array_equal(acq._compute_acq(p["Xc"][sl])[:, 0], a[sl])
+    perm = np.random.RandomState(1).permutation(2 ** 18)
+    assert np.array_equal(acq._compute_acq(p["Xc"][:2 ** 18][perm])[:, 0], a[:2 ** 18][perm])
+    om = oracle_model(p)
+    Xs = p["Xc"][:2048]
+    marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], Xs, 1)
+    ref = oacq.aggregate(marg, p["use_full_support"], p["prob"])[:, 0]
+    check_close(a[:2048], ref, "S full-size subset")
+    assert np.argmax(a[:2048]) == np.argmax(ref)
