@@ -23,7 +23,7 @@ VAR_CLIP = 2
 # every symbol include/bopl_b200.h declares
 SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", "bopl_build_info", "bopl_set_model",
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
-           "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_topk",
+           "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
            "bopl_uei_host", "bopl_launch_count"]
 
 
@@ -93,6 +93,7 @@ def load():
     lib.bopl_uei.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, vp]
     lib.bopl_uei_grad.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, dp, vp]
     lib.bopl_uei_affine.argtypes = [vp, dp, c_int, dp, c_int, dp, dp, c_int, dp, dp, vp]
+    lib.bopl_expected_utility.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, c_int, dp, dp, vp]
     lib.bopl_uei_constrained.argtypes = [vp, dp, c_int, dp, c_int, dp, dp, c_int, dp, dp, vp]
     lib.bopl_topk.argtypes = [vp, dp, c_int, c_int, c_ll, dp, llp, vp]
     lib.bopl_uei_host.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, c_int, c_ll,

@@ -37,10 +37,28 @@ class BoxSpace(object):
         return False
 
 
+def latin_design(bounds, points_count):
+    """Centred latin hypercube as GPyOpt/experiment_design/latin_design.py:18-41 draws it through pyDOE
+    (`lhs(dim, n, criterion='center')`: one unused `np.random.rand(n, dim)`, then one `np.random.permutation` of the bin
+    centres per dimension), scaled to the bounds."""
+    dim = len(bounds)
+    cut = np.linspace(0, 1, points_count + 1)
+    np.random.rand(points_count, dim)                     # pyDOE draws it before branching on the criterion
+    centre = (cut[:points_count] + cut[1:points_count + 1]) / 2
+    H = np.zeros((points_count, dim))
+    for j in range(dim):
+        H[:, j] = np.random.permutation(centre)
+    b = np.asarray(bounds, dtype=np.float64)
+    return b[:, 0][None, :] + H * (b[:, 1] - b[:, 0])[None, :]
+
+
 def initial_design(design_type, space, init_points_count, seed=None):
-    if design_type != "random":
-        raise NotImplementedError("only the 'random' design is on the accelerated path (acquisition_optimizer.py:79)")
-    return samples_multidimensional_uniform(space.get_bounds(), init_points_count, seed)
+    if design_type == "random":
+        return samples_multidimensional_uniform(space.get_bounds(), init_points_count, seed)
+    if design_type == "latin":
+        return latin_design(space.get_bounds(), init_points_count)
+    raise NotImplementedError("only the 'random' and 'latin' designs are on the accelerated path "
+                              "(acquisition_optimizer.py:79,266)")
 
 
 class AnchorPointsGenerator(object):

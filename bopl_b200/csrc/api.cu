@@ -424,6 +424,37 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
   return BOPL_OK;
 }
 
+int bopl_expected_utility(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+                          const double* theta, int Lt, int p, const double* wts, int nH, double* val, double* dval,
+                          void* stream) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (util_kind == BOPL_UTIL_CONSTRAINED) return fail(h, BOPL_ERR_INVALID, "the constrained utility has no MC kernel");
+  if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
+  if (N == 0) return BOPL_OK;
+  if (!Xc || !Z || !theta || !wts || !val) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (dval && !h->has_winv) return fail(h, BOPL_ERR_STATE, "gradients need Winv (bopl_set_model was given NULL)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
+  if (dval && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
+  for (int hh = 0; hh < nH; ++hh) {
+    // predict_noiseless: no likelihood variance, clipped at 1e-10 (gpmodel.py:181-190)
+    if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_CLIP, st))) return rc;
+    if (dval) {
+      if ((rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
+      if ((rc = launch_uei_mc_grad(h, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, N, Z, nw, util_kind, theta, Lt, p, wts,
+                                   nullptr, 1.0, hh > 0, val, dval, st, 1)))
+        return rc;
+    } else if ((rc = launch_uei_mc(h, h->mean_s, h->var_s, N, Z, nw, util_kind, theta, Lt, p, wts, nullptr, 1.0, hh > 0,
+                                   val, st, 1))) {
+      return rc;
+    }
+  }
+  return BOPL_OK;
+}
+
 int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta, int Lt, const double* wts,
                     const double* best, int nH, double* acq, double* dacq, void* stream) {
   BOPL_CHECK_HANDLE(h);

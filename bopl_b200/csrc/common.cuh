@@ -114,11 +114,11 @@ int launch_incumbent(bopl_handle* h, const double* F, int util_kind, const doubl
                      double* best, cudaStream_t st);
 int launch_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, const double* Z, int nw, int util_kind,
                   const double* theta, int Lt, int p, const double* wts, const double* best, double scale,
-                  int accumulate, double* acq, cudaStream_t st);
+                  int accumulate, double* acq, cudaStream_t st, int plain = 0);
 int launch_uei_mc_grad(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
                        int N, const double* Z, int nw, int util_kind, const double* theta, int Lt, int p,
                        const double* wts, const double* best, double scale, int accumulate, double* acq, double* dacq,
-                       cudaStream_t st);
+                       cudaStream_t st, int plain = 0);
 int launch_uei_affine(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
                       int N, const double* theta, int Lt, const double* wts, const double* best, double scale,
                       int accumulate, double* acq, double* dacq, cudaStream_t st);

@@ -88,6 +88,7 @@ struct McParams {
   double* dacq;         // [N*d]
   double scale;
   int N, m, d, nw, Lt, p, accumulate;
+  int plain;            // 1: expected utility, sum of U itself (no incumbent, no max(.,0)); acquisition_optimizer.py:211-247
 };
 
 // Shared staging: Z [nw*m], theta [Lt*p], wts [Lt], best [Lt]
@@ -96,7 +97,7 @@ __device__ __forceinline__ void stage_small(const McParams& p, double* zs, doubl
   for (int i = threadIdx.x; i < p.Lt * p.p; i += blockDim.x) ths[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.Lt; i += blockDim.x) {
     ws[i] = p.wts[i];
-    bs[i] = p.best[i];
+    bs[i] = p.best ? p.best[i] : 0.0;
   }
   __syncthreads();
 }
@@ -138,12 +139,12 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
       for (; l + 1 < p.Lt; l += 2) {
         double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
         double u1 = utility_value<KIND, M>(a, ths + (l + 1) * p.p, m);
-        acc0 = fma(ws[l], fmax(u0 - bs[l], 0.0), acc0);
-        acc1 = fma(ws[l + 1], fmax(u1 - bs[l + 1], 0.0), acc1);
+        acc0 = fma(ws[l], p.plain ? u0 : fmax(u0 - bs[l], 0.0), acc0);
+        acc1 = fma(ws[l + 1], p.plain ? u1 : fmax(u1 - bs[l + 1], 0.0), acc1);
       }
       if (l < p.Lt) {
         double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
-        acc0 = fma(ws[l], fmax(u0 - bs[l], 0.0), acc0);
+        acc0 = fma(ws[l], p.plain ? u0 : fmax(u0 - bs[l], 0.0), acc0);
       }
       acc += acc0 + acc1;
     }
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_grad_kernel(McParams p) {
         if (j < m) a[j] = fma(sg[j], zs[k * m + j], mu[j]);
       const double* th = ths + l * p.p;
       double u = utility_value<KIND>(a, th, m);
-      acc = fma(ws[l], fmax(u - bs[l], 0.0), acc);
-      if (u > bs[l]) {   // strict, uEI.py:160
+      acc = fma(ws[l], p.plain ? u : fmax(u - bs[l], 0.0), acc);
+      if (p.plain || u > bs[l]) {   // strict, uEI.py:160
         const double w = ws[l];
 #pragma unroll
         for (int j = 0; j < MAX_M; ++j)
@@ -452,9 +453,10 @@ static int mc_grid(const bopl_handle* h, int N) {
 
 int launch_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, const double* Z, int nw, int util_kind,
                   const double* theta, int Lt, int p, const double* wts, const double* best, double scale,
-                  int accumulate, double* acq, cudaStream_t st) {
+                  int accumulate, double* acq, cudaStream_t st, int plain) {
   if (N <= 0) return BOPL_OK;
   McParams mp{};
+  mp.plain = plain;
   mp.mean = mean; mp.var = var; mp.Z = Z; mp.theta = theta; mp.wts = wts; mp.best = best; mp.acq = acq;
   mp.scale = scale; mp.N = N; mp.m = h->m; mp.d = h->d; mp.nw = nw; mp.Lt = Lt; mp.p = p; mp.accumulate = accumulate;
   size_t smem = (size_t)(nw * h->m + Lt * p + 2 * Lt) * sizeof(double);
@@ -473,9 +475,10 @@ int launch_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, 
 int launch_uei_mc_grad(bopl_handle* h, const double* mean, const double* var, const double* dmean, const double* dvar,
                        int N, const double* Z, int nw, int util_kind, const double* theta, int Lt, int p,
                        const double* wts, const double* best, double scale, int accumulate, double* acq, double* dacq,
-                       cudaStream_t st) {
+                       cudaStream_t st, int plain) {
   if (N <= 0) return BOPL_OK;
   McParams mp{};
+  mp.plain = plain;
   mp.mean = mean; mp.var = var; mp.dmean = dmean; mp.dvar = dvar; mp.Z = Z; mp.theta = theta; mp.wts = wts; mp.best = best;
   mp.acq = acq; mp.dacq = dacq;
   mp.scale = scale; mp.N = N; mp.m = h->m; mp.d = h->d; mp.nw = nw; mp.Lt = Lt; mp.p = p; mp.accumulate = accumulate;

@@ -186,6 +186,16 @@ class Engine(object):
                                              dacq.data_ptr() if with_grad else None, self._stream()))
         return acq, dacq
 
+    def expected_utility_dev(self, Xc, Z, kind, theta, wts, nH, with_grad=False):
+        N = Xc.shape[0]
+        Lt, p = theta.shape
+        val = self.empty(N)
+        dval = self.empty(N, self.d) if with_grad else None
+        self._check(self.lib.bopl_expected_utility(self.h, Xc.data_ptr(), N, Z.data_ptr(), Z.shape[0], UTILITY_KINDS[kind],
+                                                   theta.data_ptr(), Lt, p, wts.data_ptr(), nH, val.data_ptr(),
+                                                   dval.data_ptr() if with_grad else None, self._stream()))
+        return val, dval
+
     def uei_constrained_dev(self, Xc, theta, wts, best, nH, with_grad=False):
         N = Xc.shape[0]
         Lt = theta.shape[0]

@@ -163,9 +163,6 @@ class AcquisitionOptimizer(object):
 
     def __init__(self, space, model=None, utility=None, expectation_utility=None, optimizer='lbfgs', inner_optimizer='lbfgs',
                  parallel=False, n_starting=400, n_anchor=20, include_baseline_points=False, batched=True, **kwargs):
-        if include_baseline_points:
-            raise NotImplementedError("include_baseline_points (per-theta marginal argmax search, "
-                                      "acquisition_optimizer.py:87-100,139-249) is not on the accelerated path yet")
         self.space = space if hasattr(space, "get_bounds") else BoxSpace(space)
         self.model = model
         self.utility = utility
@@ -177,26 +174,140 @@ class AcquisitionOptimizer(object):
         self.n_anchor = n_anchor
         self.include_baseline_points = include_baseline_points
         self.batched = batched
+        self.number_of_utility_parameter_samples = 3                                  # acquisition_optimizer.py:38
+        if include_baseline_points and (model is None or utility is None):
+            raise ValueError("include_baseline_points needs the model and the utility")
+        if utility is not None and utility.parameter_distribution is not None:
+            self.full_parameter_support = self.utility.parameter_distribution.use_full_support
+        if model is not None:
+            self.number_of_gp_hyps_samples = min(10, self.model.number_of_hyps_samples())
+            self.n_attributes = self.model.output_dim
         self.kwargs = kwargs
         self.context_manager = ContextManager(self.space)
         self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
+        self.inner_optimizer = choose_optimizer(self.inner_optimizer_name, self.context_manager.noncontext_bounds)
         self.last_stats = {}
 
+    # ---- local optimisation from a set of anchors (serial = the reference's loop; batched = lock-step)
+    def _local_search(self, anchor_points, f, f_df, optimizer, final_f):
+        """Returns [(x (1,d), fx)] per anchor.  final_f=True re-evaluates f at the rounded optimum as `apply_optimizer`
+        does (optimizer.py:295-300); False returns L-BFGS's own value as `apply_optimizer_inner` does (:343)."""
+        if f_df is not None and self.batched and len(anchor_points) > 1:
+            results, batches = lockstep_lbfgs(list(anchor_points), f_df, optimizer.bounds, optimizer.maxiter)
+            self.last_stats = {"anchors": len(anchor_points), "f_df_batches": batches}
+            if final_f:
+                X = np.vstack([_round_optimum(self.space, r[0]) for r in results])
+                fX = np.asarray(f(X), dtype=np.float64).reshape(len(X))
+                return [(X[i:i + 1], np.atleast_2d(fX[i])) for i in range(len(X))]
+            return [(r[0], r[1] if r[1] is not None else np.atleast_2d(f(r[0]))) for r in results]
+        self.last_stats = {"anchors": len(anchor_points), "f_df_batches": None}
+        if final_f:
+            return [apply_optimizer(optimizer, a, f=f, df=None, f_df=f_df, space=self.space) for a in anchor_points]
+        out = []
+        for a in anchor_points:
+            x, fx = optimizer.optimize(np.atleast_2d(a), f, None, f_df)
+            out.append((x, fx if fx is not None else np.atleast_2d(f(x))))
+        return out
+
     def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
+        """acquisition_optimizer.py:60-137."""
+        import random
         self.f, self.df, self.f_df = f, df, f_df
         self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
         gen = ObjectiveAnchorPointsGenerator(self.space, "random", f, self.n_starting)
         anchor_points, anchor_points_values = gen.get(num_anchor=self.n_anchor, duplicate_manager=duplicate_manager,
                                                       context_manager=self.context_manager, get_scores=True)
-        if f_df is not None and self.batched and len(anchor_points) > 1:
-            results, batches = lockstep_lbfgs(list(anchor_points), f_df, self.optimizer.bounds, self.optimizer.maxiter)
-            X = np.vstack([_round_optimum(self.space, r[0]) for r in results])
-            fX = np.asarray(f(X), dtype=np.float64).reshape(len(X))          # apply_optimizer's closing f(x), batched
-            optimized_points = [(X[i:i + 1], np.atleast_2d(fX[i])) for i in range(len(X))]
-            self.last_stats = {"anchors": len(anchor_points), "f_df_batches": batches}
-        else:
-            optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, space=self.space)
-                                for a in anchor_points]
-            self.last_stats = {"anchors": len(anchor_points), "f_df_batches": None}
+        if self.include_baseline_points:                                              # :87-100
+            if self.full_parameter_support:
+                utility_parameter_samples = self.utility.parameter_distribution.support
+            else:
+                utility_parameter_samples = self.utility.parameter_distribution.sample(self.number_of_utility_parameter_samples)
+            X_baseline = np.atleast_2d([self._current_marginal_argmax(th)[0, :] for th in utility_parameter_samples])
+            fX_baseline = np.asarray(f(X_baseline))[:, 0]
+            anchor_points = np.vstack((anchor_points, X_baseline))
+            anchor_points_values = np.concatenate((np.asarray(anchor_points_values).reshape(-1), fX_baseline))
+        optimized_points = self._local_search(anchor_points, f, f_df, self.optimizer, final_f=True)
         x_min, fx_min = min(optimized_points, key=lambda t: float(np.squeeze(t[1])))
-        return x_min, np.squeeze(fx_min)
+        fx_min = np.squeeze(fx_min)
+        if self.include_baseline_points:                                              # :118-134
+            fx_min_baseline = fX_baseline.min()
+            use = fx_min_baseline < fx_min or (fx_min_baseline == fx_min and np.random.binomial(1, 0.5, 1))
+            if use:
+                index = random.choice(np.atleast_1d(np.argmin(fX_baseline)))
+                x_min = np.atleast_2d(X_baseline[index, :])
+                fx_min = fX_baseline[index]
+        return x_min, fx_min
+
+    # ---- argmax_x E_n[U(f(x)) | theta]  (acquisition_optimizer.py:139-249)
+    def marginal_objective(self, parameter, Z_samples=None):
+        """The (f, f_df) pair the reference builds inside `_current_marginal_argmax`: minus the expected utility of the
+        NOISELESS posterior under the fixed parameter, summed (not averaged) over hyper-samples and draws.
+        affine utility: theta . posterior mean (:145-187); ExpectationUtility callables: evaluated on the host from the
+        GPU's predict_noiseless and gradients (:189-209); otherwise 50 fixed N(0,1) draws (:211-247)."""
+        model, eng = self.model, self.model.engine
+        n_h = self.number_of_gp_hyps_samples
+        m = self.n_attributes
+        theta = np.ascontiguousarray(np.asarray(parameter, dtype=np.float64).reshape(1, -1))
+        if self.utility.affine or self.expectation_utility is None:
+            if self.utility.affine:
+                kind, Z = "linear", np.zeros((1, m))
+                if theta.shape[1] != m:
+                    raise ValueError("affine utility needs one parameter per attribute")
+            else:
+                kind = self.utility.resolve_kind(m, theta[0])
+                Z = np.random.normal(size=(50, m)) if Z_samples is None else np.asarray(Z_samples, dtype=np.float64)
+            th_d, Z_d, w_d = eng.to_dev(theta), eng.to_dev(Z), eng.to_dev(np.ones(1))
+
+            def val_func(X):
+                X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+                val, _ = eng.expected_utility_dev(eng.to_dev(X), Z_d, kind, th_d, w_d, n_h, False)
+                model.set_hyperparameters(n_h - 1)
+                return -val.cpu().numpy().reshape(-1, 1)
+
+            def val_func_with_gradient(X):
+                X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+                val, dval = eng.expected_utility_dev(eng.to_dev(X), Z_d, kind, th_d, w_d, n_h, True)
+                model.set_hyperparameters(n_h - 1)
+                return -val.cpu().numpy().reshape(-1, 1), -dval.cpu().numpy().reshape(X.shape)
+            return val_func, val_func_with_gradient
+
+        eu = self.expectation_utility
+
+        def val_func(X):
+            X = np.atleast_2d(X)
+            func_val = np.zeros((X.shape[0], 1))
+            for h in range(n_h):
+                model.set_hyperparameters(h)
+                mean, var = model.predict_noiseless(X)
+                for i in range(X.shape[0]):
+                    func_val[i, 0] += eu.func(parameter, mean[:, i], var[:, i])
+            return -func_val
+
+        def val_func_with_gradient(X):
+            X = np.atleast_2d(X)
+            func_val = np.zeros((X.shape[0], 1))
+            func_gradient = np.zeros(X.shape)
+            for h in range(n_h):
+                model.set_hyperparameters(h)
+                mean, var = model.predict_noiseless(X)
+                aux = np.concatenate((model.posterior_mean_gradient(X), model.posterior_variance_gradient(X)))
+                for i in range(X.shape[0]):
+                    func_val[i, 0] += eu.func(parameter, mean[:, i], var[:, i])
+                    func_gradient[i, :] += np.matmul(eu.gradient(parameter, mean[:, i], var[:, i]), aux[:, i])
+            return -func_val, -func_gradient
+        return val_func, val_func_with_gradient
+
+    def _current_marginal_argmax(self, parameter):
+        f, f_df = self.marginal_objective(parameter)
+        return self.optimize_inner_func(f=f, f_df=f_df)[0]
+
+    def optimize_inner_func(self, f=None, df=None, f_df=None, duplicate_manager=None, n_starting=400, n_anchor=20):
+        """acquisition_optimizer.py:251-281: latin design -> anchors -> L-BFGS per anchor -> best (value as returned by
+        L-BFGS, `apply_optimizer_inner`)."""
+        self.inner_optimizer = choose_optimizer(self.inner_optimizer_name, self.context_manager.noncontext_bounds)
+        gen = ObjectiveAnchorPointsGenerator(self.space, "latin", f, n_starting)
+        anchor_points, _ = gen.get(num_anchor=n_anchor, duplicate_manager=duplicate_manager,
+                                   context_manager=self.context_manager, get_scores=True)
+        optimized_points = self._local_search(anchor_points, f, f_df, self.inner_optimizer, final_f=False)
+        x_min, fx_min = min(optimized_points, key=lambda t: float(np.squeeze(t[1])))
+        return x_min, fx_min

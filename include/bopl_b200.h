@@ -133,6 +133,15 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
                   const double* theta, int Lt, int p, const double* wts, const double* best, int nH,
                   double* acq, double* dacq, void* stream);
 
+/* Expected utility under the noiseless posterior (no incumbent, no improvement clamp, NOT normalised — the reference sums):
+ *   val[i] = sum_{h < nH} sum_l wts[l] sum_k U(mean^h[:,i] + sqrt(var_noiseless^h[:,i]) * Z[k,:], theta_l),  dval [N*d] or NULL.
+ * Replaces the objective of AcquisitionOptimizer._current_marginal_argmax: optimization_services/
+ * acquisition_optimizer.py:211-247 (MC branch, Z = 50 fixed draws); the affine branch (:145-187) is the same call with
+ * the linear utility and Z = one row of zeros. */
+int bopl_expected_utility(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, int util_kind,
+                          const double* theta, int Lt, int p, const double* wts, int nH, double* val, double* dval,
+                          void* stream);
+
 /* Closed-form EI of a linear utility: acq [N], dacq [N*d] or NULL.  theta [Lt*m], best [nH*Lt].
  * value path (dacq == NULL): uEI_affine._marginal_acq + _get_quantiles, uEI_affine.py:73-89,127-142 (sigma floor 1e-10);
  * gradient path: uEI_affine._marginal_acq_with_gradient, uEI_affine.py:91-116 (no floor).                       */

@@ -346,6 +346,37 @@ def uei_constrained_marginal_with_gradient_loop(model, func, thetas, X, n_h):
     return marginal / n_h, marginal_d / n_h
 
 
+# ----------------------------------------------------------------------------- marginal expected utility (baseline points)
+def marginal_objective_loop(model, func, gradient, parameter, Z_samples, X, n_h, affine=False):
+    """The val_func / val_func_with_gradient closures of AcquisitionOptimizer._current_marginal_argmax
+    (bopl/optimization_services/acquisition_optimizer.py:145-187 affine, :211-247 MC): returns (-value (N,1), -gradient (N,d))."""
+    X = np.atleast_2d(X)
+    m = model.output_dim
+    func_val = np.zeros((X.shape[0], 1))
+    func_gradient = np.zeros(X.shape)
+    for h in range(n_h):
+        model.set_hyperparameters(h)
+        if affine:
+            muX = model.posterior_mean(X)
+            dmu_dX = model.posterior_mean_gradient(X)
+            func_val += np.reshape(np.matmul(parameter, muX), (X.shape[0], 1))
+            func_gradient += np.tensordot(parameter, dmu_dX, axes=1)
+            continue
+        mean, var = model.predict_noiseless(X)
+        std = np.sqrt(var)
+        dmean_dX = model.posterior_mean_gradient(X)
+        dstd_dX = model.posterior_variance_gradient(X)
+        for i in range(X.shape[0]):
+            for j in range(m):
+                dstd_dX[j, i, :] /= (2 * std[j, i])
+            for Z in Z_samples:
+                aux1 = mean[:, i] + np.multiply(Z, std[:, i])
+                func_val[i, 0] += func(aux1, parameter)
+                aux2 = dmean_dX[:, i, :] + np.multiply(dstd_dX[:, i, :].T, Z).T
+                func_gradient[i, :] += np.matmul(gradient(aux1, parameter), aux2)
+    return -func_val, -func_gradient
+
+
 # ----------------------------------------------------------------------------- anchor selection
 def top_k(neg_acq, k):
     """GPyOpt/optimization/anchor_points_generator.py:58-62 on scores = -acq (acquisitions/base.py:40).

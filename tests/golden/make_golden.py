@@ -351,6 +351,59 @@ def main_constrained():
         print("wrote uEIc_%s.npz  acq range [%.3e, %.3e]" % (name, out["acq_value"].min(), out["acq_value"].max()))
 
 
+MARGINAL_CASES = [  # (problem, kwargs, experiment script with the utility callables, affine flag)
+    ("dtlz1a_linear", dict(N=10, n=30, n_w=6, L=3, H=2), "test_dtlz1a_linear.py", True),
+    ("dtlz2a_quad", dict(N=10, n=30, n_w=6, L=8, H=2), "test_dtlz2a_quad.py", False),
+    ("vlmop3_exp", dict(N=10, n=30, n_w=6, L=3, H=1), "test_vlmop3_exp.py", False),
+]
+
+
+def main_marginal():
+    """The objective closures of the reference's AcquisitionOptimizer._current_marginal_argmax (the baseline-point search,
+    acquisition_optimizer.py:139-249), captured by intercepting `optimize_inner_func`, evaluated on the test candidates."""
+    from bopl_b200.synthetic import make_problem
+    R = build_reference()
+    for name in ["aux_software.GPyOpt.experiment_design", "aux_software.GPyOpt.optimization",
+                 "aux_software.GPyOpt.optimization.optimizer", "aux_software.GPyOpt.optimization.anchor_points_generator"]:
+        _pkg(name)
+    sys.modules["aux_software.GPyOpt.experiment_design"].initial_design = None
+    om = sys.modules["aux_software.GPyOpt.optimization.optimizer"]
+    om.apply_optimizer = om.apply_optimizer_inner = None
+    om.choose_optimizer = lambda name, bounds: None
+    ag = sys.modules["aux_software.GPyOpt.optimization.anchor_points_generator"]
+    ag.ObjectiveAnchorPointsGenerator = ag.ThompsonSamplingAnchorPointsGenerator = None
+    AO = _load("ref_acquisition_optimizer", os.path.join(REF, "bopl/optimization_services/acquisition_optimizer.py")).AcquisitionOptimizer
+    for name, kw, script, affine in MARGINAL_CASES:
+        p = make_problem(name, **kw)
+        model = reference_model(R, p)
+        func, grad = R.exp_utils(script, p["m"])
+        theta = p["theta"]
+        dist = R.UtilityDistribution(prior_sample_generator=lambda n_s, seed=None: theta[:n_s], utility_func=func,
+                                     use_full_support=False)
+        util = R.Utility(func=func, gradient=grad, parameter_distribution=dist, affine=affine)
+        space = types.SimpleNamespace(model_dimensionality=p["d"], config_space_expanded=[None] * p["d"],
+                                      get_bounds=lambda: [(p["lo"], p["hi"])] * p["d"])
+        opt = AO(space, model, util)
+        opt.number_of_gp_hyps_samples = p["H"]
+        got = {}
+
+        def capture(f=None, df=None, f_df=None, **k):
+            got["f"], got["f_df"] = f, f_df
+            return np.zeros((1, p["d"])), 0.0
+        opt.optimize_inner_func = capture
+        out = dict(name=name, acq="marginal", N=kw["N"], n=kw["n"], n_w=kw["n_w"], L=kw["L"], H=kw["H"], affine=affine,
+                   Xc=p["Xc"], theta=theta)
+        for l in range(min(2, len(theta))):
+            np.random.seed(1234 + l)                      # the MC branch draws its 50 Z samples from the global stream
+            opt._current_marginal_argmax(theta[l])
+            out["f_%d" % l] = got["f"](p["Xc"].copy())
+            v, dv = got["f_df"](p["Xc"].copy())
+            out["fdf_f_%d" % l], out["fdf_df_%d" % l] = v, dv
+        np.savez(os.path.join(HERE, "marginal_%s.npz" % name), **out)
+        print("wrote marginal_%s.npz  value range [%.3e, %.3e]" % (name, out["f_0"].min(), out["f_0"].max()))
+
+
 if __name__ == "__main__":
     main()
     main_constrained()
+    main_marginal()

@@ -457,3 +457,49 @@ def test_full_size_config_S_properties_and_subset_parity():
     ref = oacq.aggregate(marg, p["use_full_support"], p["prob"])[:, 0]
     check_close(a[:2048], ref, "S full-size subset")
     assert np.argmax(a[:2048]) == np.argmax(ref)
+
+
+@pytest.mark.parametrize("fname", _golden("marginal_"))
+def test_marginal_objective_against_reference_generated_golden(fname):
+    """E_n[U(f(x)) | theta] of the baseline-point search (acquisition_optimizer.py:139-249): CUDA path vs the closures of
+    the reference's own AcquisitionOptimizer._current_marginal_argmax."""
+    import os
+    from bopl_b200.optimization import AcquisitionOptimizer
+    from tests.helpers import make_utility
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname), allow_pickle=False)
+    name, H = str(g["name"]), int(g["H"])
+    p = make_problem(name, N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=H)
+    gm = gpu_model(p)
+    util = make_utility(p)
+    util.affine = bool(g["affine"])
+    opt = AcquisitionOptimizer([(p["lo"], p["hi"])] * p["d"], model=gm, utility=util)
+    for l in range(2):
+        np.random.seed(1234 + l)
+        Z = np.random.normal(size=(50, p["m"]))
+        f, f_df = opt.marginal_objective(p["theta"][l], Z_samples=Z)
+        check_close(f(p["Xc"]), g["f_%d" % l], fname + " f")
+        v, dv = f_df(p["Xc"])
+        check_close(v, g["fdf_f_%d" % l], fname + " f_df value")
+        check_close(dv, g["fdf_df_%d" % l], fname + " f_df gradient", rtol=1e-7)
+
+
+def test_optimizer_with_baseline_points_end_to_end():
+    """include_baseline_points=True: per-theta marginal argmax search (latin design + lock-step L-BFGS on the GPU objective),
+    baseline points appended to the anchors, acquisition optimised from all of them."""
+    from bopl_b200.optimization import AcquisitionOptimizer
+    p = make_problem("dtlz2a_quad", N=400)
+    gm = gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    np.random.seed(3)
+    opt = AcquisitionOptimizer(acq.space, model=gm, utility=acq.utility, n_starting=200, n_anchor=4, include_baseline_points=True)
+    acq.optimizer = opt
+    x, fx = acq.optimize()
+    b = np.asarray(acq.space.get_bounds())
+    assert x.shape == (1, p["d"]) and np.all(x >= b[:, 0]) and np.all(x <= b[:, 1]) and np.isfinite(fx)
+    assert float(fx) <= float(acq.acquisition_function(x)[0, 0]) + 1e-9
+    # the marginal argmax improves on every latin starting point's expected utility
+    f, f_df = opt.marginal_objective(p["theta"][0])
+    xm, fm = opt.optimize_inner_func(f=f, f_df=f_df, n_starting=100, n_anchor=5)
+    np.random.seed(11)
+    from bopl_b200.anchor_points import latin_design
+    assert float(np.squeeze(fm)) <= float(f(latin_design(acq.space.get_bounds(), 100)).min()) + 1e-9

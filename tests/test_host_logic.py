@@ -221,5 +221,14 @@ def test_acquisition_optimizer_host_path_returns_best_local_optimum():
         opt = AcquisitionOptimizer(BoxSpace([(0, 1)] * 3), n_starting=50, n_anchor=5, batched=batched)
         x, fx = opt.optimize(f=f, f_df=f_df)
         assert x.shape == (1, 3) and np.allclose(x, 0.7, atol=1e-5) and fx < 1e-9
-    with pytest.raises(NotImplementedError):
-        AcquisitionOptimizer(BoxSpace([(0, 1)] * 3), include_baseline_points=True)
+    with pytest.raises(ValueError):
+        AcquisitionOptimizer(BoxSpace([(0, 1)] * 3), include_baseline_points=True)     # needs model + utility
+
+
+def test_latin_design_is_a_centred_latin_hypercube():
+    from bopl_b200.anchor_points import latin_design
+    np.random.seed(4)
+    X = latin_design([(0.0, 1.0), (-2.0, 2.0)], 10)
+    assert X.shape == (10, 2)
+    assert np.allclose(np.sort(X[:, 0]), (np.arange(10) + 0.5) / 10)
+    assert np.allclose(np.sort(X[:, 1]), -2 + 4 * (np.arange(10) + 0.5) / 10)

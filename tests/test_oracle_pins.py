@@ -179,6 +179,20 @@ def test_oracle_against_reference_generated_golden(fname):
     """Fixtures made by running the reference's own uEI.py / uEI_affine.py code (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, fname), allow_pickle=False)
     name, H = str(g["name"]), int(g["H"])
+    if str(g["acq"]) == "marginal":
+        p = make_problem(name, N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=H)
+        assert np.array_equal(p["Xc"], g["Xc"]) and np.array_equal(p["theta"], g["theta"])
+        om = oracle_model(p)
+        func, grad = utilities.get(p["utility"], p["m"])
+        for l in range(2):
+            np.random.seed(1234 + l)
+            Z = np.random.normal(size=(50, p["m"]))
+            v, dv = oacq.marginal_objective_loop(om, func, grad, p["theta"][l], Z, p["Xc"], H, affine=bool(g["affine"]))
+            sc = np.abs(g["fdf_f_%d" % l]).max()
+            assert np.allclose(v, g["f_%d" % l], rtol=1e-10, atol=1e-12 * sc)
+            assert np.allclose(v, g["fdf_f_%d" % l], rtol=1e-10, atol=1e-12 * sc)
+            assert np.allclose(dv, g["fdf_df_%d" % l], rtol=1e-8, atol=1e-10 * np.abs(g["fdf_df_%d" % l]).max())
+        return
     if str(g["acq"]) == "uEI_constrained":
         p = make_problem(name, N=int(g["N"]), n=int(g["n"]), L=int(g["L"]), H=H, utility="constrained")
         assert np.array_equal(p["Xc"], g["Xc"]) and np.array_equal(p["theta"], g["theta"])
