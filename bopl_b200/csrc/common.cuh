@@ -48,6 +48,7 @@ struct bopl_handle {
   long long launches = 0;
   int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
   int* sm_slots = nullptr;
+  size_t attr_smem[4] = {0, 0, 0, 0};  // dynamic-smem attribute already set on THIS device, per posterior-kernel instantiation
   int trsm_variant = 3;                // BOPL_TRSM_VARIANT: 3 candidate-owning warps, diagonal solve in registers (default);
                                        // 1 row-owning 128x128 tiles, one CTA per SM; 2 row-owning 128x64 tiles, two CTAs per SM
   // model storage

@@ -347,7 +347,7 @@ int launch_cfg(bopl_handle* h, TrsmParams& p, cudaStream_t st) {
     p.stagger_cycles = (long long)(0.4 * (double)Cfg::BC * h->n_pad * (h->n_pad + 128.0) / 2.0 / 32.0);
   }
   size_t smem = Cfg::smem_bytes(h->d);
-  static size_t attr_smem = 0;
+  size_t& attr_smem = h->attr_smem[Cfg::MINB == 2 ? 2 : 3];   // function attributes are per device: remember per handle
   if (smem > attr_smem) {
     BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

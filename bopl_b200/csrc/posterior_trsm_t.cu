@@ -292,7 +292,7 @@ int launch_t(bopl_handle* h, TParams& p, cudaStream_t st) {
   if (rc) return rc;
   p.scratch = h->trsm_scratch;
   size_t smem = t_smem_bytes<STAGES>(h->d);
-  static size_t attr_smem = 0;
+  size_t& attr_smem = h->attr_smem[STAGES == 4 ? 0 : 1];   // function attributes are per device: remember per handle
   if (smem > attr_smem) {
     BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_t_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
