@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
         }
       }
 
+      // A warp cannot leave a main loop of >= STAGES steps before every thread has issued its share of a refill, i.e.
+      // before every warp is past phase a — that orders the next block row's staging writes after these reads.  Short
+      // loops (block row 0, tiny n) have no such hand-off: barrier explicitly (the condition is CTA-uniform).
+      if (nsteps < STAGES) __syncthreads();
+
       // ---- main loop: acc[cand][row] += V^T[cand][k] * (-L)^T[k][row] over the already-solved rows
       for (int it = 0; it < nsteps; ++it) {
         const unsigned gt = g0 + it, st_c = gt % STAGES;
