@@ -162,6 +162,7 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_TRSM_VARIANT")) h->trsm_variant = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
+  if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
@@ -231,7 +232,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   std::vector<double> Lp((size_t)n_pad * n_pad);
   std::vector<double> Dinv((size_t)nblk * TRSM_BM * TRSM_BM);
   std::vector<double> DinvFrag((size_t)nblk * 136 * 64);
-  std::vector<double> Xs((size_t)n_pad * d), al((size_t)n_pad);
+  std::vector<double> Xs((size_t)n_pad * d), al((size_t)n_pad), SBlk((size_t)n_pad * (d + 1));
   h->gp_host.resize((size_t)m * H);
   for (int g = 0; g < m * H; ++g) {
     const double* L = L_h + (size_t)g * n * n;
@@ -264,10 +265,11 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       for (int q = 0; q < d; ++q) Xs[(size_t)(pad + i) * d + q] = X_h[(size_t)i * d + q] / ell[q];   // stationary.py:161-162
       al[pad + i] = alpha_h[(size_t)g * n + i];
     }
+    pack_stage_blocks(Xs.data(), al.data(), n_pad, d, SBlk.data());
     GpDev gp{};
-    double *pL, *pD, *pF, *pX, *pa, *pe, *pW = nullptr;
+    double *pL, *pD, *pF, *pX, *pa, *pe, *pS, *pW = nullptr;
     if ((rc = dev_upload(h, Lp.data(), Lp.size(), &pL)) || (rc = dev_upload(h, Dinv.data(), Dinv.size(), &pD)) ||
-        (rc = dev_upload(h, DinvFrag.data(), DinvFrag.size(), &pF)) ||
+        (rc = dev_upload(h, DinvFrag.data(), DinvFrag.size(), &pF)) || (rc = dev_upload(h, SBlk.data(), SBlk.size(), &pS)) ||
         (rc = dev_upload(h, Xs.data(), Xs.size(), &pX)) || (rc = dev_upload(h, al.data(), al.size(), &pa)) ||
         (rc = dev_upload(h, ell, (size_t)d, &pe))) {
       free_model(h);
@@ -286,6 +288,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     gp.Lneg = pL;
     gp.Dinv = pD;
     gp.DinvFrag = pF;
+    gp.StageBlk = pS;
     gp.Xs = pX;
     gp.alpha = pa;
     gp.ell = pe;

@@ -23,6 +23,7 @@ constexpr int SMALL_N = 32;     // batches up to this size take the matrix-vecto
 struct GpDev {
   const double* Lneg;    // [n_pad*n_pad] front-padded factor, off-diagonal 128-blocks NEGATED (acc += (-L)·V); diagonal blocks unused
   const double* Dinv;    // [n_pad/128][128][128] inverses of the diagonal blocks (lower triangular)
+  const double* StageBlk;  // [n_pad/128][(d+1)*128] per block: scaled training rows transposed [q][128], then alpha[128]
   const double* DinvFrag;  // [n_pad/128][136*64] the same inverses packed as DMMA B fragments (posterior_trsm_t.cu)
   const double* Xs;      // [n_pad*d] training inputs divided by the lengthscales, front-padded with zeros
   const double* alpha;   // [n_pad] woodbury vector, front-padded with zeros
@@ -46,6 +47,7 @@ struct bopl_handle {
   double* small_scratch = nullptr; size_t small_scratch_bytes = 0;
   std::string err;
   long long launches = 0;
+  int trsm_stages = 3;                 // BOPL_TRSM_STAGES=4: deeper pipeline when shared memory allows (measured no faster)
   int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
   int* sm_slots = nullptr;
   size_t attr_smem[4] = {0, 0, 0, 0};  // dynamic-smem attribute already set on THIS device, per posterior-kernel instantiation
@@ -102,6 +104,7 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st);
 void pack_dinv_fragments(const double* Dinv_block, double* out);
+void pack_stage_blocks(const double* Xs, const double* alpha, int n_pad, int d, double* out);
 bool use_small_path(const bopl_handle* h, int N);
 int launch_posterior_small(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                            cudaStream_t st);

@@ -37,7 +37,7 @@ struct TParams {
 
 template <int STAGES>
 __host__ __device__ constexpr size_t t_smem_bytes(int d) {
-  return (size_t)(STAGES * STAGE_DBL + DFRAG_DBL + 2 * TRSM_BM * d + TRSM_BM) * sizeof(double);
+  return (size_t)(STAGES * STAGE_DBL + DFRAG_DBL + TRSM_BM * d + 2 * TRSM_BM * (d + 1)) * sizeof(double);
 }
 
 template <int STAGES>
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
   double* P = smem;                                // pipeline stages
   double* DF = P + STAGES * STAGE_DBL;             // Dinv B fragments of the current block row
   double* xc_s = DF + DFRAG_DBL;                   // [d][128]  candidates / lengthscale
-  double* xt_s = xc_s + TRSM_BM * d;               // [d][128]  training rows of the block / lengthscale
-  double* alpha_s = xt_s + TRSM_BM * d;            // [128]
+  double* SB = xc_s + TRSM_BM * d;                 // [2][(d+1)*128]  staged block: training rows^T / lengthscale, alpha
+  const int SB_DBL = TRSM_BM * (d + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -59,8 +59,10 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
 
   double* Vt = p.scratch + (size_t)blockIdx.x * TRSM_BM * n_pad;   // [128 cands][n_pad] solved panel of this CTA
 
-  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], df_bar;
+  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], df_bar, sb_bar[2];
   if (tid == 0) {
+    mbar_init(&sb_bar[0], NT);
+    mbar_init(&sb_bar[1], NT);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], NT);
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
   __syncthreads();
   unsigned g0 = 0;       // running index of the pipeline tiles issued so far
   unsigned dfc = 0;      // running count of Dinv-fragment loads
+  unsigned bc = 0;       // running count of staged blocks (buffer = bc & 1)
 
   for (int item = blockIdx.x; item < p.m * p.ntiles; item += gridDim.x) {
     const int j = item / p.ntiles, tile = item - j * p.ntiles;
@@ -87,19 +90,27 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
       xc_s[q * TRSM_BM + c] = p.Xc[(size_t)cc * d + q] / gp.ell[q];
     }
 
+    // staged block 0 of this item (the buffer's last readers are two block rows back, behind the barrier above)
+    for (int idx = tid; idx < SB_DBL / 2; idx += NT) cp_async16(SB + (bc & 1) * SB_DBL + 2 * idx, gp.StageBlk + 2 * idx);
+    cp_async_mbar_arrive(&sb_bar[bc & 1]);
+
     double mu[2] = {0.0, 0.0}, ss[2] = {0.0, 0.0};
     double acc[2][16][2];
 
     for (int ib = 0; ib < nblk; ++ib) {
       const int R0 = ib * TRSM_BM;
-      for (int idx = tid; idx < TRSM_BM * d; idx += NT) {
-        int r = idx / d, q = idx - r * d;
-        xt_s[q * TRSM_BM + r] = gp.Xs[(size_t)R0 * d + idx];
-      }
-      for (int idx = tid; idx < TRSM_BM; idx += NT) alpha_s[idx] = gp.alpha[R0 + idx];
+      const double* xt_s = SB + (bc & 1) * SB_DBL;          // [d][128] training rows of the block / lengthscale
+      const double* alpha_s = xt_s + TRSM_BM * d;           // [128]
+      mbar_wait(&sb_bar[bc & 1], (bc >> 1) & 1);            // prefetched during the previous block row
       __threadfence_block();
-      __syncthreads();  // S1: staging visible; the previous block row's V stores are ordered before the loads below;
-                        //     every warp is past the previous diagonal solve -> DF and all stages are free
+      __syncthreads();  // S1: the previous block row's V stores are ordered before the loads below; every warp is past
+                        //     the previous diagonal solve and K* generation -> DF, all stages and the other SB are free
+      if (ib + 1 < nblk) {                                  // next block's rows travel while this block row computes
+        const double* src = gp.StageBlk + (size_t)(ib + 1) * SB_DBL;
+        double* dst = SB + ((bc + 1) & 1) * SB_DBL;
+        for (int idx = tid; idx < SB_DBL / 2; idx += NT) cp_async16(dst + 2 * idx, src + 2 * idx);
+        cp_async_mbar_arrive(&sb_bar[(bc + 1) & 1]);
+      }
 
       // ---- prefetch: Dinv fragments of this block row and the first pipeline tiles
       {
@@ -228,18 +239,27 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
             for (int mi = 0; mi < 2; ++mi) tmp[u][mi][0] = tmp[u][mi][1] = 0.0;
 #pragma unroll
           for (int kt = 0; kt <= 4 * G + 3; ++kt) {
+            // fragments of the (up to four) blocks of this k-step first, then all the k-even DMMAs, then all the k-odd ones:
+            // consecutive DMMAs never hit the same accumulator
+            double2 b[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u)
               if (kt <= 4 * G + u) {
-                const double2 b = frag[32 * fi];
+                b[u] = frag[32 * fi];
                 ++fi;
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
-                  dmma(tmp[u][mi][0], tmp[u][mi][1], acc[mi][kt][0], b.x);
-                  dmma(tmp[u][mi][0], tmp[u][mi][1], acc[mi][kt][1], b.y);
-                }
               }
-            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kt <= 4 * G + u) {
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) dmma(tmp[u][mi][0], tmp[u][mi][1], acc[mi][kt][0], b[u].x);
+              }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kt <= 4 * G + u) {
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) dmma(tmp[u][mi][0], tmp[u][mi][1], acc[mi][kt][1], b[u].y);
+              }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -263,6 +283,7 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
           if (publish)
             *reinterpret_cast<double2*>(Vt + (size_t)(Cw + 8 * mi + g) * n_pad + R0 + 8 * nt + 2 * t) = make_double2(v0, v1);
         }
+      ++bc;
     }
 
     // ---- finalize the item: the four t-lanes of a candidate hold its partial sums
@@ -327,6 +348,18 @@ void pack_dinv_fragments(const double* Dinv_block /*128x128 row-major*/, double*
       }
 }
 
+// Host-side packing of the per-block staging arrays: [nblk][(d+1)*128] = scaled training rows transposed [q][128], alpha[128].
+void pack_stage_blocks(const double* Xs /*n_pad*d*/, const double* alpha /*n_pad*/, int n_pad, int d, double* out) {
+  const int nblk = n_pad / TRSM_BM;
+  for (int b = 0; b < nblk; ++b) {
+    double* o = out + (size_t)b * TRSM_BM * (d + 1);
+    for (int r = 0; r < TRSM_BM; ++r) {
+      for (int q = 0; q < d; ++q) o[(size_t)q * TRSM_BM + r] = Xs[(size_t)(b * TRSM_BM + r) * d + q];
+      o[(size_t)d * TRSM_BM + r] = alpha[b * TRSM_BM + r];
+    }
+  }
+}
+
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
@@ -343,7 +376,7 @@ int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, d
   p.n_pad = h->n_pad;
   p.pad = h->pad;
   p.flags = flags;
-  if (t_smem_bytes<4>(h->d) + 256 <= 227 * 1024) return launch_t<4>(h, p, st);
+  if (h->trsm_stages == 4 && t_smem_bytes<4>(h->d) + 256 <= 227 * 1024) return launch_t<4>(h, p, st);
   return launch_t<3>(h, p, st);
 }
 
