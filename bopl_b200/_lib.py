@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
 SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}

@@ -1,7 +1,9 @@
 // api.cu — the C-ABI of libbopl_b200.so (include/bopl_b200.h): handle lifetime, model upload and the entry points
 // that sequence the kernels.  Plain pointers and sizes only; every entry returns a bopl_status.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -244,14 +246,28 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       const double* src = L + (size_t)i * n;
       for (int k = 0; k <= i; ++k) row[k] = src[k];
     }
-    for (int b = 0; b < nblk; ++b)
-      if (!invert_lower_block(Lp.data() + (size_t)b * TRSM_BM * n_pad + (size_t)b * TRSM_BM, n_pad, TRSM_BM,
-                              Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM)) {
+    {  // the nblk diagonal-block inversions (extended precision) are independent: spread them over the host cores
+      std::atomic<int> next(0), bad(0);
+      auto work = [&]() {
+        for (int b = next.fetch_add(1); b < nblk; b = next.fetch_add(1)) {
+          if (!invert_lower_block(Lp.data() + (size_t)b * TRSM_BM * n_pad + (size_t)b * TRSM_BM, n_pad, TRSM_BM,
+                                  Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM)) {
+            bad.store(1);
+            continue;
+          }
+          pack_dinv_fragments(Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM, DinvFrag.data() + (size_t)b * 136 * 64);
+        }
+      };
+      const int nthr = std::max(1, std::min<int>(nblk, (int)std::thread::hardware_concurrency()));
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+      work();
+      for (auto& th : pool) th.join();
+      if (bad.load()) {
         free_model(h);
         return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
       }
-    for (int b = 0; b < nblk; ++b)
-      pack_dinv_fragments(Dinv.data() + (size_t)b * TRSM_BM * TRSM_BM, DinvFrag.data() + (size_t)b * 136 * 64);
+    }
     // negate the off-diagonal blocks so that the kernel's update is a pure accumulate: acc += (-L) V
     for (int i = 0; i < n_pad; ++i) {
       const int bi = i / TRSM_BM;

@@ -103,6 +103,7 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
                           cudaStream_t st);
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st);
+bool trsm_t_fits(int d);
 void pack_dinv_fragments(const double* Dinv_block, double* out);
 void pack_stage_blocks(const double* Xs, const double* alpha, int n_pad, int d, double* out);
 bool use_small_path(const bopl_handle* h, int N);

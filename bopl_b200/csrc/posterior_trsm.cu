@@ -364,7 +364,9 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
                           cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
   if (use_small_path(h, N)) return launch_posterior_small(h, Xc, N, hsel, mean, var, flags, st);
-  if (h->trsm_variant != 1 && h->trsm_variant != 2) return launch_posterior_trsm_t(h, Xc, N, hsel, mean, var, flags, st);
+  // default: the candidate-owning kernel; wider inputs (d > 20) do not fit its shared-memory plan -> row-owning form
+  if (h->trsm_variant != 1 && h->trsm_variant != 2 && trsm_t_fits(h->d))
+    return launch_posterior_trsm_t(h, Xc, N, hsel, mean, var, flags, st);
   TrsmParams p;
   p.gps = h->gp_dev;
   p.Xc = Xc;
@@ -378,7 +380,7 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
   p.n_pad = h->n_pad;
   p.pad = h->pad;
   p.flags = flags;
-  if (h->trsm_variant == 2) return launch_cfg<TrsmCfg<64, 3, 8>>(h, p, st);
+  if (h->trsm_variant == 2) return launch_cfg<TrsmCfg<64, 3, 8>>(h, p, st);   // two CTAs per SM (A/B only)
   return launch_cfg<TrsmCfg<128, 4, 16>>(h, p, st);
 }
 

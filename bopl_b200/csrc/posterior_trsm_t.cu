@@ -360,6 +360,9 @@ void pack_stage_blocks(const double* Xs /*n_pad*d*/, const double* alpha /*n_pad
   }
 }
 
+// The candidate-owning kernel keeps the staged inputs of two block rows in shared memory: it fits up to d = 20.
+bool trsm_t_fits(int d) { return t_smem_bytes<3>(d) + 256 <= 227 * 1024; }
+
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st) {
   if (N <= 0) return BOPL_OK;

@@ -503,3 +503,39 @@ def test_optimizer_with_baseline_points_end_to_end():
     np.random.seed(11)
     from bopl_b200.anchor_points import latin_design
     assert float(np.squeeze(fm)) <= float(f(latin_design(acq.space.get_bounds(), 100)).min()) + 1e-9
+
+
+@pytest.mark.parametrize("d,m", [(1, 1), (20, 7), (23, 2), (24, 16)])
+def test_wide_inputs_and_many_attributes(d, m):
+    """Shape limits of the kernels: d up to 24 inputs (d > 20 takes the row-owning posterior kernel), m up to 16 attributes."""
+    from oracle.gp import ExactGP, MultiOutputGPOracle
+    from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
+    rs = np.random.RandomState(d * 100 + m)
+    n, N = 150, 300
+    X = rs.uniform(size=(n, d))
+    Y = np.stack([np.sin(X @ rs.normal(size=d)) + 0.1 * rs.normal(size=n) for _ in range(m)])
+    ell = rs.uniform(0.8, 1.6, size=(m, 1, d)) * np.sqrt(d)
+    var = rs.uniform(0.5, 2.0, size=(m, 1))
+    noise = np.full((m, 1), 1e-4)
+    Xc = rs.uniform(size=(N, d))
+    om = MultiOutputGPOracle([[ExactGP(X, Y[j], "Mat52", var[j, 0], ell[j, 0], noise[j, 0])] for j in range(m)])
+    gm = MultiOutputGP.from_state(state_from_hyperparameters(X, Y, ["Mat52"] * m, var, ell, noise))
+    mu_o, v_o = om.predict(Xc)
+    mu_g, v_g = gm.predict(Xc)
+    check_close(mu_g, mu_o, "mean d=%d m=%d" % (d, m))
+    floor = variance_floor(om, Xc)
+    assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor)
+    check_close(gm.posterior_mean_gradient(Xc[:40]), om.posterior_mean_gradient(Xc[:40]), "dmean")
+    check_dvar(gm.posterior_variance_gradient(Xc[:40]), om, Xc[:40], "dvar")
+    # MC acquisition with m attributes (m > 6 takes the generic-m kernel instantiation)
+    theta = rs.dirichlet(np.ones(m), 5)
+    Z = rs.normal(size=(9, m))
+    p = dict(d=d, m=m, lo=0.0, hi=1.0, theta=theta, Z=Z, prob=None, use_full_support=False, utility="linear", H=1)
+    acq = gpu_acquisition(p, gm)
+    marg = oacq.uei_marginal_vec(om, "linear", theta, Z, Xc, 1)
+    check_close(acq._compute_acq(Xc), oacq.aggregate(marg, False, None), "uEI d=%d m=%d" % (d, m))
+    f, df = acq._compute_acq_withGradients(Xc[:10])
+    fm, dm = oacq.uei_marginal_with_gradient_vec(om, "linear", theta, Z, Xc[:10], 1)
+    check_close(f, oacq.aggregate(fm, False, None), "uEI f")
+    # 150 points on a line with lengthscale ~1 is a cond(Ky) ~ 1e6+ model: beta = -2 K* Winv cancels accordingly
+    check_close(df, oacq.aggregate_gradient(dm, False, None), "uEI df", rtol=1e-8 if d > 1 else 1e-6)
