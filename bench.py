@@ -201,7 +201,7 @@ def run_gpu(args):
         val, idx = step(True)
     t1.record()
     barrier()
-    launches = eng.launch_count - launches0 + args.steps    # + the flush fill kernel per step
+    launches = eng.launch_count - launches0                 # this library's kernels only (the L2-flush fill is torch's)
     elapsed = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     trsm = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in trsm_ms]))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -246,7 +246,7 @@ def run_gpu(args):
             "config": {"workload": "S: d=10 m=3 n=%d N=%d candidates per GPU, n_w=%d L=%d H=1 Matern52-ARD noise=1e-6 linear utility, top-%d anchors"
                                    % (w["n"], N, w["n_w"], w["L"], K_ANCHOR),
                        "sharding": "candidates row-sharded, %d per rank; all-gather of top-%d records only" % (N, K_ANCHOR),
-                       "l2": "working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2; 256 MB flush write between steps"},
+                       "l2": "working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2, and a 256 MB flush write between steps"},
             "clocks": sampler.summary(),
             "e2e": {"value": evals_per_step / float(e2e_t.item()), "unit": UNIT,
                     "h2d_bytes_per_step": int(N * d * 8 + (p["Z"].size + theta.size + 2 * len(theta)) * 8),
