@@ -1,0 +1,153 @@
+"""Host-side hyper-parameter inference for one attribute's GP — what `GPyOpt/models/gpmodel.py:109-149` does with GPy:
+MAP estimate (`model.optimize(max_iters=200)`), 1 % multiplicative jitter, then HMC (`GPy/inference/mcmc/hmc.py:30-68`:
+n_burnin + n_samples * subsample_interval iterations of `leapfrog_steps` leap-frog steps, Metropolis accept), keeping
+every `subsample_interval`-th draw after burn-in as the hyper-samples.
+
+This is NOT on the accelerated path (the model-fit side stays on the host, as in the reference) and
+it is not a bit-for-bit restatement of GPy's optimiser either — MCMC output is a random draw in both.  It exists so
+that `MultiOutputGP.updateModel(X, Y)` works without pre-supplied hyper-samples, i.e. so that a BO loop written against
+the reference runs end to end.  Same model as the reference's default: Matern52 ARD (or the named kernel), variance and
+lengthscales positive through GPy's Logexp transform (softplus), Gamma(E=2, V=4) priors on every positive
+hyper-parameter (gpmodel.py:71-72), Gaussian noise fixed at 1e-6 (`exact_feval`), fixed at `noise_var`, or free and
+initialised at 0.01 Var(Y) (gpmodel.py:67,75-80), mean-centred targets (this fork's normaliser).
+"""
+import numpy as np
+from scipy.linalg import lapack
+from scipy.special import gammaln
+
+_SQRT3, _SQRT5 = np.sqrt(3.0), np.sqrt(5.0)
+_GAMMA_A, _GAMMA_B = 1.0, 0.5                      # Gamma.from_EV(2, 4): shape E^2/V, rate E/V
+
+
+def _softplus(x):
+    return np.logaddexp(0.0, x)
+
+
+def _softplus_inv(t):
+    return np.where(t > 30.0, t, np.log(np.expm1(np.minimum(t, 30.0))))
+
+
+def _kernel_and_grads(kind, variance, ell, X):
+    """K(X, X) and dK/d(variance), dK/d(ell_q) for the stationary kernels of the path (GPy/kern/src/stationary.py)."""
+    n, d = X.shape
+    Xs = X / ell
+    sq = np.sum(Xs * Xs, 1)
+    r2 = np.clip(sq[:, None] + sq[None, :] - 2.0 * Xs @ Xs.T, 0.0, np.inf)
+    np.fill_diagonal(r2, 0.0)
+    r = np.sqrt(r2)
+    if kind == "Mat52":
+        e = np.exp(-_SQRT5 * r)
+        K = variance * (1.0 + _SQRT5 * r + 5.0 / 3.0 * r2) * e
+        dK_dr_over_r = variance * (-5.0 / 3.0) * (1.0 + _SQRT5 * r) * e           # (dK/dr) / r
+    elif kind == "Mat32":
+        e = np.exp(-_SQRT3 * r)
+        K = variance * (1.0 + _SQRT3 * r) * e
+        dK_dr_over_r = -3.0 * variance * e
+    elif kind in ("rbf", "ExpQuad"):
+        K = variance * np.exp(-0.5 * r2)
+        dK_dr_over_r = -K
+    else:
+        raise ValueError("unsupported kernel %r" % (kind,))
+    # dr/d ell_q = -(x_q - x'_q)^2 / (ell_q^3 r)  =>  dK/d ell_q = -(dK/dr)/r * (x_q - x'_q)^2 / ell_q^3
+    dK_dell = []
+    for q in range(d):
+        dq = X[:, q][:, None] - X[:, q][None, :]
+        dK_dell.append(-dK_dr_over_r * dq * dq / ell[q] ** 3)
+    return K, K / variance, dK_dell
+
+
+class GPObjective(object):
+    """Negative log posterior of the hyper-parameters in the unconstrained (softplus-inverse) parametrisation."""
+
+    def __init__(self, X, Y, kind="Mat52", ARD=True, noise_fixed=None):
+        self.X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64).reshape(len(self.X), 1)
+        self.Yc = Y - Y.mean()
+        self.Yvar = float(Y.var())
+        self.kind, self.ARD, self.noise_fixed = kind, ARD, noise_fixed
+        self.n, self.d = self.X.shape
+        self.n_ell = self.d if ARD else 1
+        self.size = 1 + self.n_ell + (0 if noise_fixed is not None else 1)
+
+    def unpack(self, x):
+        th = _softplus(np.asarray(x, dtype=np.float64))
+        variance = th[0]
+        ell = th[1:1 + self.n_ell] if self.ARD else np.repeat(th[1], self.d)
+        noise = self.noise_fixed if self.noise_fixed is not None else th[-1]
+        return variance, ell, noise
+
+    def initial(self):
+        th = [1.0] + [1.0] * self.n_ell + ([] if self.noise_fixed is not None else [max(0.01 * self.Yvar, 1e-8)])
+        return _softplus_inv(np.array(th))
+
+    def value_and_grad(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        th = _softplus(x)
+        variance, ell, noise = self.unpack(x)
+        K, dK_dvar, dK_dell = _kernel_and_grads(self.kind, variance, ell, self.X)
+        Ky = K.copy()
+        Ky[np.diag_indices_from(Ky)] += noise + 1e-8
+        L, info = lapack.dpotrf(Ky, lower=1)
+        if info != 0:
+            return 1e25, np.zeros_like(x)
+        alpha = lapack.dpotrs(L, self.Yc, lower=1)[0]
+        Kinv = lapack.dpotri(L, lower=1)[0]
+        Kinv = np.tril(Kinv) + np.tril(Kinv, -1).T
+        ll = -0.5 * float((self.Yc.T @ alpha).item()) - np.sum(np.log(np.diag(L))) - 0.5 * self.n * np.log(2 * np.pi)
+        dL_dK = 0.5 * (alpha @ alpha.T - Kinv)
+        g_th = [np.sum(dL_dK * dK_dvar)]
+        gl = [np.sum(dL_dK * dk) for dk in dK_dell]
+        g_th += gl if self.ARD else [float(np.sum(gl))]
+        if self.noise_fixed is None:
+            g_th.append(np.trace(dL_dK))
+        g_th = np.array(g_th)
+        # Gamma(a, b) log prior on every positive hyper-parameter
+        lp = np.sum(_GAMMA_A * np.log(_GAMMA_B) - gammaln(_GAMMA_A) + (_GAMMA_A - 1.0) * np.log(th) - _GAMMA_B * th)
+        g_th = g_th + ((_GAMMA_A - 1.0) / th - _GAMMA_B)
+        dth_dx = 1.0 / (1.0 + np.exp(-x))                       # derivative of softplus
+        return -(ll + lp), -(g_th * dth_dx)
+
+
+def map_estimate(obj, max_iters=200):
+    import scipy.optimize
+    res = scipy.optimize.minimize(obj.value_and_grad, obj.initial(), jac=True, method="L-BFGS-B",
+                                  options={"maxiter": max_iters})
+    return res.x
+
+
+def hmc_sample(obj, x0, num_samples, hmc_iters=20, stepsize=1e-1, rng=np.random):
+    """GPy/inference/mcmc/hmc.py:30-68 with M = I."""
+    x = np.array(x0, dtype=np.float64)
+    out = np.empty((num_samples, x.size))
+    f, g = obj.value_and_grad(x)
+    for i in range(num_samples):
+        p = rng.normal(size=x.size)
+        H_old = f + 0.5 * float(p @ p)
+        x_new, f_new, g_new = x.copy(), f, g
+        for _ in range(hmc_iters):
+            p = p - 0.5 * stepsize * g_new
+            x_new = x_new + stepsize * p
+            f_new, g_new = obj.value_and_grad(x_new)
+            p = p - 0.5 * stepsize * g_new
+        H_new = f_new + 0.5 * float(p @ p)
+        if np.isfinite(H_new) and (H_old > H_new or rng.rand() < np.exp(H_old - H_new)):
+            x, f, g = x_new, f_new, g_new
+        out[i] = x
+    return out
+
+
+def fit_hyperparameter_samples(X, Y, kind="Mat52", ARD=True, exact_feval=False, noise_var=None, n_samples=10, n_burnin=100,
+                               subsample_interval=10, step_size=1e-1, leapfrog_steps=20, max_iters=200, hmc=True, rng=np.random):
+    """Returns (variance (H,), lengthscale (H,d), noise (H,)) — the hyper-samples of one attribute (gpmodel.py:109-149).
+    hmc=False: the MAP estimate only (H = 1)."""
+    noise_fixed = 1e-6 if exact_feval else noise_var
+    obj = GPObjective(X, Y, kind, ARD, noise_fixed)
+    x_map = map_estimate(obj, max_iters)
+    if not hmc:
+        xs = x_map[None, :]
+    else:
+        th = _softplus(x_map) * (1.0 + rng.normal(size=x_map.size) * 0.01)           # gpmodel.py:124
+        ss = hmc_sample(obj, _softplus_inv(th), n_burnin + n_samples * subsample_interval, leapfrog_steps, step_size, rng)
+        xs = ss[n_burnin::subsample_interval][:n_samples]
+    unp = [obj.unpack(x) for x in xs]
+    return (np.array([u[0] for u in unp]), np.array([u[1] for u in unp]), np.array([float(u[2]) for u in unp]))

@@ -5,8 +5,10 @@ sm_100a kernels through the C-ABI; the per-attribute Python loop of the referenc
 225-246) is replaced by one launch over all attributes.  What stays on the host is what the reference keeps in
 LAPACK once per model update — the Cholesky factorisation (`exact_gaussian_inference.py:44-51`), `dpotrs`, `dpotri`.
 
-Hyper-parameter inference (MAP + HMC, `GPyOpt/models/gpmodel.py:109-149`) is outside the hot path: supply the
-hyper-samples with `set_hyperparameter_samples(...)`, or wrap a live reference model with `from_reference_model`.
+Hyper-parameter inference (MAP + HMC, `GPyOpt/models/gpmodel.py:109-149`) is outside the hot path and stays on the
+host: `updateModel` runs `bopl_b200/fit.py` (same model, priors and sampler settings as the reference) unless the
+hyper-samples were supplied with `set_hyperparameter_samples(...)`; a live reference model can be wrapped with
+`from_reference_model`.
 """
 import numpy as np
 from scipy.linalg import lapack
@@ -144,7 +146,7 @@ class MultiOutputGP(object):
     analytical_gradient_prediction = True
 
     def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
-                 fixed_hyps=False, device=0, gradients=True):
+                 fixed_hyps=False, device=0, gradients=True, fit_options=None):
         self.output_dim = output_dim
         self.kernel = [None] * output_dim if kernel is None else kernel          # GPy kernel names ('Mat52', 'rbf', ...)
         self.noise_var = [None] * output_dim if noise_var is None else noise_var
@@ -154,6 +156,7 @@ class MultiOutputGP(object):
         self.fixed_hyps = fixed_hyps
         self.name = 'multi-output GP'                                              # checked in core/bopl.py:46,440
         self.gradients = gradients
+        self.fit_options = dict(fit_options or {})        # n_burnin, subsample_interval, step_size, leapfrog_steps, max_iters
         self.engine = Engine(device)
         self._hyps = None
         self._h = 0
@@ -200,12 +203,28 @@ class MultiOutputGP(object):
 
     def updateModel(self, X_all, Y_all):
         """multi_outputGP.py:57-62.  Refits every (attribute, hyper-sample) posterior on the host with LAPACK and uploads."""
-        if self._hyps is None:
-            raise NotImplementedError("hyper-parameter inference (MAP + HMC) is outside the accelerated path: call "
-                                      "set_hyperparameter_samples(...) first, or use from_reference_model(...)")
         self.X_all, self.Y_all = X_all, Y_all
-        kinds, variance, lengthscale, noise = self._hyps
+        if self._hyps is not None:
+            kinds, variance, lengthscale, noise = self._hyps
+        else:
+            kinds, variance, lengthscale, noise = self._infer_hyperparameters(X_all, Y_all)
         self._load(state_from_hyperparameters(X_all, Y_all, kinds, variance, lengthscale, noise, self.gradients))
+
+    def _infer_hyperparameters(self, X_all, Y_all):
+        """Per attribute: MAP + HMC hyper-samples on the host (GPyOpt/models/gpmodel.py:109-149); `fixed_hyps=True` keeps
+        the MAP estimate only."""
+        from .fit import fit_hyperparameter_samples
+        X = np.asarray(X_all, dtype=np.float64)
+        m, d = self.output_dim, X.shape[1]
+        H = 1 if self.fixed_hyps else self.n_samples
+        kinds = np.array([k if k is not None else "Mat52" for k in self.kernel])
+        variance, lengthscale, noise = np.empty((m, H)), np.empty((m, H, d)), np.empty((m, H))
+        for j in range(m):
+            v, l, s = fit_hyperparameter_samples(X, Y_all[j], str(kinds[j]), bool(self.ARD[j]), bool(self.exact_feval[j]),
+                                                 self.noise_var[j], n_samples=H, hmc=not self.fixed_hyps, **self.fit_options)
+            variance[j], lengthscale[j], noise[j] = v, l, s
+        self.n_samples = H
+        return kinds, variance, lengthscale, noise
 
     # ---- reference surface
     def number_of_hyps_samples(self):

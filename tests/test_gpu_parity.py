@@ -539,3 +539,19 @@ def test_wide_inputs_and_many_attributes(d, m):
     check_close(f, oacq.aggregate(fm, False, None), "uEI f")
     # 150 points on a line with lengthscale ~1 is a cond(Ky) ~ 1e6+ model: beta = -2 K* Winv cancels accordingly
     check_close(df, oacq.aggregate_gradient(dm, False, None), "uEI df", rtol=1e-8 if d > 1 else 1e-6)
+
+
+def test_bo_loop_end_to_end_with_host_fit():
+    """examples/dtlz1a_linear.py: updateModel (host MAP + HMC) -> uEI.update_samples -> AcquisitionOptimizer -> new point,
+    three iterations; the incumbent true utility never decreases and every suggestion is inside the box."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "dtlz1a_linear.py")
+    spec = importlib.util.spec_from_file_location("dtlz1a_linear_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    X, Y, hist = mod.run(iterations=3, seed=1, n_samples=2,
+                         fit_options=dict(n_burnin=6, subsample_interval=2, leapfrog_steps=5, max_iters=50), verbose=False)
+    assert X.shape == (14 + 3, 6) and Y.shape == (2, 17)
+    assert np.all(X >= 0.0) and np.all(X <= 1.0) and np.all(np.isfinite(Y))
+    assert all(b >= a for a, b in zip(hist, hist[1:]))
