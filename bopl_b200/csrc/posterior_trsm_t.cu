@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
       g0 += (unsigned)nsteps;
 
       // ---- diagonal block, in registers and in place: V^T[:, nt] = sum_{kt <= nt} rhs^T[:, kt] * Dinv^T[kt, nt]
+      const bool publish = (ib + 1 < nblk);
       mbar_wait(&df_bar, dfc & 1);
       ++dfc;
       {
@@ -261,28 +262,24 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
                 for (int mi = 0; mi < 2; ++mi) dmma(tmp[u][mi][0], tmp[u][mi][1], acc[mi][kt][1], b[u].y);
               }
           }
+          // write the finished tiles back in place; their sum of squares and their publication for the following block
+          // rows (16-byte stores, 64 B per candidate) overlap the DMMAs of the next group
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
-              acc[mi][4 * G + u][0] = tmp[u][mi][0];
-              acc[mi][4 * G + u][1] = tmp[u][mi][1];
+              const double v0 = tmp[u][mi][0], v1 = tmp[u][mi][1];
+              acc[mi][4 * G + u][0] = v0;
+              acc[mi][4 * G + u][1] = v1;
+              ss[mi] = fma(v0, v0, ss[mi]);
+              ss[mi] = fma(v1, v1, ss[mi]);
+              if (publish)
+                *reinterpret_cast<double2*>(Vt + (size_t)(Cw + 8 * mi + g) * n_pad + R0 + 8 * (4 * G + u) + 2 * t) =
+                    make_double2(v0, v1);
             }
         }
       }
 
-      // ---- column square-sums; publish V^T for the following block rows (16-byte stores, 64 B per candidate)
-      const bool publish = (ib + 1 < nblk);
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-          const double v0 = acc[mi][nt][0], v1 = acc[mi][nt][1];
-          ss[mi] = fma(v0, v0, ss[mi]);
-          ss[mi] = fma(v1, v1, ss[mi]);
-          if (publish)
-            *reinterpret_cast<double2*>(Vt + (size_t)(Cw + 8 * mi + g) * n_pad + R0 + 8 * nt + 2 * t) = make_double2(v0, v1);
-        }
       ++bc;
     }
 
