@@ -59,14 +59,24 @@ class _UtilityAcquisition(AcquisitionBase):
     analytical_gradient_prediction = True
 
     def _thetas(self):
-        th = np.asarray(self.utility_parameter_samples, dtype=np.float64)
-        L = len(self.utility_parameter_samples)
-        return np.ascontiguousarray(th.reshape(L, -1))
+        src = self.utility_parameter_samples
+        if isinstance(src, np.ndarray) and src.dtype == np.float64 and src.ndim == 2 and src.flags.c_contiguous:
+            return src                                         # same object -> its device copy is reused
+        th = np.asarray(src, dtype=np.float64)
+        return np.ascontiguousarray(th.reshape(len(src), -1))
 
     def _weights(self, L):
         if self.use_full_support:                              # uEI.py:56-57
             return np.ascontiguousarray(self.utility_prob_dist, dtype=np.float64).reshape(L)
         return np.full(L, 1.0 / L)                             # uEI.py:59
+
+    def _dev_weights(self, wts):
+        """Uniform weights 1/L: one cached device vector per L."""
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        key = ("uniform", len(wts))
+        if key not in cache or self.use_full_support:
+            cache[key] = (None, self.model.engine.to_dev(wts))
+        return cache[key][1]
 
     def _incumbents(self, kind, theta_dev, per_h):
         """(n_h, L) device tensor of best-so-far utilities.  per_h=False replicates the model's current h."""
@@ -79,6 +89,18 @@ class _UtilityAcquisition(AcquisitionBase):
 
     def _x(self, X):
         return np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+
+    def _dev(self, name, array):
+        """Device copy of a small host array that only changes in `update_samples` (W_samples, theta, weights): uploaded
+        once per array OBJECT — the L-BFGS inner loop calls thousands of times between two updates.  Arrays replaced by
+        assignment are picked up (identity check); arrays mutated in place must be re-assigned."""
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        hit = cache.get(name)
+        if hit is not None and hit[0] is array:
+            return hit[1]
+        t = self.model.engine.to_dev(array)
+        cache[name] = (array, t)
+        return t
 
 
 class uEI(_UtilityAcquisition):
@@ -100,10 +122,10 @@ class uEI(_UtilityAcquisition):
             self.utility_parameter_samples = self.utility.sample_parameter(10)
 
     def _prepare(self, per_h):
-        eng = self.model.engine
         theta = self._thetas()
         kind = self.utility.resolve_kind(self.n_attributes, theta[0])
-        th_d = eng.to_dev(theta)
+        th_d = self._dev("theta", self.utility_parameter_samples) if theta is self.utility_parameter_samples \
+            else self.model.engine.to_dev(theta)
         best = self._incumbents(kind, th_d, per_h)
         return kind, theta, th_d, self._weights(len(theta)), best
 
@@ -133,7 +155,9 @@ class uEI(_UtilityAcquisition):
         eng = self.model.engine
         n_h = self.number_of_gp_hyps_samples
         kind, theta, th_d, wts, best = self._prepare(per_h=False)
-        acq, dacq = eng.uei_grad_dev(eng.to_dev(X), eng.to_dev(self.W_samples), kind, th_d, eng.to_dev(wts), best, n_h)
+        w_src = self.utility_prob_dist if self.use_full_support else None
+        w_d = self._dev("wts", w_src) if w_src is not None and wts is w_src else self._dev_weights(wts)
+        acq, dacq = eng.uei_grad_dev(eng.to_dev(X), self._dev("Z", self.W_samples), kind, th_d, w_d, best, n_h)
         self.model.set_hyperparameters(n_h - 1)
         return acq.cpu().numpy().reshape(X.shape[0], 1), dacq.cpu().numpy().reshape(X.shape)
 

@@ -286,34 +286,59 @@ __global__ void __launch_bounds__(256) small_kstar_kernel(SmallParams p) {
 }
 
 // out[j][c][i] = scale * sum_k M_j[i][k] K[j][c][k];  TRI: M = Linv (k <= i), scale 1;  else M = Winv, scale -2.
-template <bool TRI>
+// Block = 8 warps = 8 consecutive rows i of M; the K* rows of ALL candidates go through shared memory in k-tiles of 128,
+// so M is streamed once whatever the batch size, with four independent 256-byte loads per warp and tile in flight.
+// Each (candidate, row) sum runs over k in a fixed order (lane-strided, tiles ascending, xor-shuffle tree) that does
+// not depend on the other candidates in the batch.
+constexpr int GV_KT = 128;
+template <bool TRI, int NC>
 __global__ void __launch_bounds__(256) small_gemv_kernel(SmallParams p) {
+  __shared__ double Ks[NC][GV_KT];
   const int j = blockIdx.y;
   const GpDev& gp = p.gps[j * p.H + p.hsel];
-  const int n = p.n, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const double* Mrow = (TRI ? gp.Linv : gp.Winv) + (size_t)i * n;
-  const int kend = TRI ? i + 1 : n;
-  double* out = TRI ? p.V : p.B;
-  for (int c0 = 0; c0 < p.N; c0 += 8) {
-    double acc[8];
+  const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 8, i = i0 + warp;
+  const double* M = TRI ? gp.Linv : gp.Winv;
+  const double* Mrow = M + (size_t)min(i, n - 1) * n;
+  const int kend = TRI ? min(i0 + 8, n) : n;          // the block's last row bounds the k-range of a triangular factor
+  const double* Kj = p.K + (size_t)j * p.N * n;
+  double acc[NC];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-    for (int k = lane; k < kend; k += 32) {
-      const double mv = Mrow[k];
+  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  for (int k0 = 0; k0 < kend; k0 += GV_KT) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NC * GV_KT; idx += 256) {
+      const int c = idx / GV_KT, kk = idx - c * GV_KT;
+      Ks[c][kk] = (c < p.N && k0 + kk < n) ? Kj[(size_t)c * n + k0 + kk] : 0.0;
+    }
+    __syncthreads();
+    double mv[GV_KT / 32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (c0 + u < p.N) acc[u] = fma(mv, p.K[((size_t)j * p.N + c0 + u) * n + k], acc[u]);
+    for (int u = 0; u < GV_KT / 32; ++u) {
+      const int k = k0 + lane + 32 * u;
+      mv[u] = (k < n && (!TRI || k <= i)) ? Mrow[k] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      double v = acc[u];
+    for (int u = 0; u < GV_KT / 32; ++u)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && c0 + u < p.N) out[((size_t)j * p.N + c0 + u) * n + i] = (TRI ? 1.0 : -2.0) * v;
-    }
+      for (int c = 0; c < NC; ++c) acc[c] = fma(mv[u], Ks[c][lane + 32 * u], acc[c]);
   }
+  double* out = (TRI ? p.V : p.B) + (size_t)j * p.N * n;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && c < p.N && i < n) out[(size_t)c * n + i] = (TRI ? 1.0 : -2.0) * v;
+  }
+}
+
+template <bool TRI>
+void launch_small_gemv(const SmallParams& p, int n, int m, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, m);
+  if (p.N <= 8) small_gemv_kernel<TRI, 8><<<grid, 256, 0, st>>>(p);
+  else if (p.N <= 16) small_gemv_kernel<TRI, 16><<<grid, 256, 0, st>>>(p);
+  else small_gemv_kernel<TRI, 32><<<grid, 256, 0, st>>>(p);
 }
 
 // mean = K* alpha + ymean, var = variance - sum V^2 (+noise, clip).  One block per (candidate, attribute), fixed order.
@@ -491,7 +516,7 @@ int launch_posterior_small(bopl_handle* h, const double* Xc, int N, int hsel, do
   small_kstar_kernel<false><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "small_kstar_kernel");
   if (var) {
-    small_gemv_kernel<true><<<dim3((h->n + 7) / 8, h->m), 256, 0, st>>>(p);
+    launch_small_gemv<true>(p, h->n, h->m, st);
     BOPL_LAUNCH_CHECK(h, "small_gemv_kernel<Linv>");
   }
   small_reduce_kernel<<<dim3(N, h->m), 256, 0, st>>>(p);
@@ -509,7 +534,7 @@ static int launch_posterior_grad_small(bopl_handle* h, const double* Xc, int N, 
   small_kstar_kernel<true><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "small_kstar_kernel<G>");
   if (dvar) {
-    small_gemv_kernel<false><<<dim3((h->n + 7) / 8, h->m), 256, 0, st>>>(p);
+    launch_small_gemv<false>(p, h->n, h->m, st);
     BOPL_LAUNCH_CHECK(h, "small_gemv_kernel<Winv>");
   }
   small_contract_kernel<<<dim3(N, h->m), GC_NT, 0, st>>>(p);
