@@ -165,6 +165,8 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
+  if (const char* v = getenv("BOPL_TRSM_KEEP_BLOCKS")) h->trsm_keep_blocks = atoi(v);
+  if (const char* v = getenv("BOPL_TRSM_L2_HINTS")) h->trsm_l2_hints = atoi(v);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;

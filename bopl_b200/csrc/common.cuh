@@ -48,9 +48,13 @@ struct bopl_handle {
   std::string err;
   long long launches = 0;
   int trsm_stages = 3;                 // BOPL_TRSM_STAGES=4: deeper pipeline when shared memory allows (measured no faster)
+  double trsm_l2_keep_frac = 0.75;     // share of the L2 the posterior kernel may pin (factor + first panel block rows)
+  int trsm_keep_blocks = -1;           // BOPL_TRSM_KEEP_BLOCKS: panel block rows per CTA kept in L2 (-1: from the budget)
   int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
   int* sm_slots = nullptr;
-  size_t attr_smem[4] = {0, 0, 0, 0};  // dynamic-smem attribute already set on THIS device, per posterior-kernel instantiation
+  size_t attr_smem[4] = {0, 0, 0, 0};
+  size_t attr_smem_t[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  int trsm_l2_hints = 1;               // BOPL_TRSM_L2_HINTS: 0 none, 1 eviction-priority hints on the L / V tile loads, 2 also on the V stores  // dynamic-smem attribute already set on THIS device, per posterior-kernel instantiation
   int trsm_variant = 3;                // BOPL_TRSM_VARIANT: 3 candidate-owning warps, diagonal solve in registers (default);
                                        // 1 row-owning 128x128 tiles, one CTA per SM; 2 row-owning 128x64 tiles, two CTAs per SM
   // model storage

@@ -8,6 +8,27 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
 }
+// L2 eviction-priority hints (createpolicy): the solved-V panels (148 x 2 MB) do not fit the 126 MB L2; keeping the most
+// re-read part (the first block rows of every panel, and the shared factor L) resident and streaming the rest cuts the
+// DRAM re-reads of the posterior kernel.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, unsigned long long pol) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "l"(pol));
+}
+__device__ __forceinline__ void st_global_v2_hint(double* gdst, double a, double b, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(gdst), "d"(a), "d"(b), "l"(pol));
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -50,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 // Copy a ROWS x KW tile of doubles (row stride `ld` doubles in global) into shared memory as [row][KW].
 // KW == 16: 16-byte chunks XOR-swizzled with (row & 1) << 2 (conflict-free LDS.128 fragments); KW == 8: plain.
+template <int ROWS, int KW, int NT>
+__device__ __forceinline__ void load_tile_hint(double* dst, const double* src, size_t ld, int tid, unsigned long long pol) {
+  constexpr int CPR = KW / 2;
+  constexpr int PER = ROWS * CPR / NT;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    int idx = tid + NT * u;
+    int row = idx / CPR, c = idx % CPR;
+    int cs = (KW == 16) ? (c ^ ((row & 1) << 2)) : c;
+    cp_async16_hint(dst + row * KW + (cs << 1), src + (size_t)row * ld + 2 * c, pol);
+  }
+}
+
 template <int ROWS, int KW, int NT>
 __device__ __forceinline__ void load_tile(double* dst, const double* src, size_t ld, int tid) {
   constexpr int CPR = KW / 2;                       // 16-byte chunks per row

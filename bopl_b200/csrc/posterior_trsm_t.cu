@@ -33,6 +33,7 @@ struct TParams {
   double* var;
   double* scratch;
   int H, hsel, m, N, d, n_pad, pad, ntiles, flags;
+  int keep_tiles;   // V k-tiles (16 rows each) below this index are kept in L2 (evict_last); the rest is streamed
 };
 
 template <int STAGES>
@@ -40,7 +41,7 @@ __host__ __device__ constexpr size_t t_smem_bytes(int d) {
   return (size_t)(STAGES * STAGE_DBL + DFRAG_DBL + TRSM_BM * d + 2 * TRSM_BM * (d + 1)) * sizeof(double);
 }
 
-template <int STAGES>
+template <int STAGES, int HINTS>
 __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
   extern __shared__ __align__(128) double smem[];
   const int d = p.d, n_pad = p.n_pad;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   unsigned g0 = 0;       // running index of the pipeline tiles issued so far
   unsigned dfc = 0;      // running count of Dinv-fragment loads
   unsigned bc = 0;       // running count of staged blocks (buffer = bc & 1)
@@ -124,8 +126,14 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
       for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nsteps) {
           const unsigned gs = (g0 + s) % STAGES;
-          load_tile<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL, Lrow + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid);
-          load_tile<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL + TILE, Vt + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid);
+          if (HINTS) {
+            load_tile_hint<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL, Lrow + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid, pol_keep);
+            load_tile_hint<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL + TILE, Vt + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid,
+                                                 (kt0 + s) < p.keep_tiles ? pol_keep : pol_stream);
+          } else {
+            load_tile<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL, Lrow + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid);
+            load_tile<TRSM_BM, TRSM_BK, NT>(P + gs * STAGE_DBL + TILE, Vt + (size_t)(kt0 + s) * TRSM_BK, n_pad, tid);
+          }
           cp_async_mbar_arrive(&full_bar[gs]);
         }
       }
@@ -208,8 +216,14 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
                 const unsigned gn = g0 + nxt, st_n = gn % STAGES;
                 if (it > 0) mbar_wait(&empty_bar[st_n], ((gn / STAGES) - 1) & 1);
                 double* stp = P + st_n * STAGE_DBL;
-                load_tile<TRSM_BM, TRSM_BK, NT>(stp, Lrow + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid);
-                load_tile<TRSM_BM, TRSM_BK, NT>(stp + TILE, Vt + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid);
+                if (HINTS) {
+                  load_tile_hint<TRSM_BM, TRSM_BK, NT>(stp, Lrow + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid, pol_keep);
+                  load_tile_hint<TRSM_BM, TRSM_BK, NT>(stp + TILE, Vt + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid,
+                                                       (kt0 + nxt) < p.keep_tiles ? pol_keep : pol_stream);
+                } else {
+                  load_tile<TRSM_BM, TRSM_BK, NT>(stp, Lrow + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid);
+                  load_tile<TRSM_BM, TRSM_BK, NT>(stp + TILE, Vt + (size_t)(kt0 + nxt) * TRSM_BK, n_pad, tid);
+                }
                 cp_async_mbar_arrive(&full_bar[st_n]);
               }
             }
@@ -273,9 +287,11 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
               acc[mi][4 * G + u][1] = v1;
               ss[mi] = fma(v0, v0, ss[mi]);
               ss[mi] = fma(v1, v1, ss[mi]);
-              if (publish)
-                *reinterpret_cast<double2*>(Vt + (size_t)(Cw + 8 * mi + g) * n_pad + R0 + 8 * (4 * G + u) + 2 * t) =
-                    make_double2(v0, v1);
+              if (publish) {
+                double* dst = Vt + (size_t)(Cw + 8 * mi + g) * n_pad + R0 + 8 * (4 * G + u) + 2 * t;
+                if (HINTS == 2) st_global_v2_hint(dst, v0, v1, (R0 / TRSM_BK) < p.keep_tiles ? pol_keep : pol_stream);
+                else *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+              }
             }
         }
       }
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(NT, 1) posterior_trsm_t_kernel(TParams p) {
   }
 }
 
-template <int STAGES>
+template <int STAGES, int HINTS>
 int launch_t(bopl_handle* h, TParams& p, cudaStream_t st) {
   p.ntiles = (p.N + TRSM_BM - 1) / TRSM_BM;
   long long items = (long long)p.ntiles * h->m;
@@ -314,13 +330,24 @@ int launch_t(bopl_handle* h, TParams& p, cudaStream_t st) {
   int rc = ensure_bytes(h, (void**)&h->trsm_scratch, &h->trsm_scratch_bytes, need);
   if (rc) return rc;
   p.scratch = h->trsm_scratch;
+  {
+    // L2 budget: the shared factor of the running attribute stays resident; of what is left (a fraction of the L2 size
+    // the device reports) every CTA keeps the first block rows of its solved panel — the ones re-read most often.
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
+    const double budget = (h->trsm_l2_keep_frac * (double)l2 - (double)h->n_pad * h->n_pad * 8.0 * 0.55) / grid;
+    long long blocks = (long long)(budget / ((double)TRSM_BM * TRSM_BM * 8.0));
+    if (h->trsm_keep_blocks >= 0) blocks = h->trsm_keep_blocks;
+    blocks = std::max<long long>(0, std::min<long long>(blocks, h->n_pad / TRSM_BM));
+    p.keep_tiles = (int)blocks * (TRSM_BM / TRSM_BK);
+  }
   size_t smem = t_smem_bytes<STAGES>(h->d);
-  size_t& attr_smem = h->attr_smem[STAGES == 4 ? 0 : 1];   // function attributes are per device: remember per handle
+  size_t& attr_smem = h->attr_smem_t[STAGES == 4 ? 0 : 1][HINTS];   // function attributes are per device: remember per handle
   if (smem > attr_smem) {
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_t_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_t_kernel<STAGES, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  posterior_trsm_t_kernel<STAGES><<<grid, NT, smem, st>>>(p);
+  posterior_trsm_t_kernel<STAGES, HINTS><<<grid, NT, smem, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "posterior_trsm_t_kernel");
   return BOPL_OK;
 }
@@ -376,8 +403,10 @@ int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, d
   p.n_pad = h->n_pad;
   p.pad = h->pad;
   p.flags = flags;
-  if (h->trsm_stages == 4 && t_smem_bytes<4>(h->d) + 256 <= 227 * 1024) return launch_t<4>(h, p, st);
-  return launch_t<3>(h, p, st);
+  if (h->trsm_stages == 4 && t_smem_bytes<4>(h->d) + 256 <= 227 * 1024) return launch_t<4, 0>(h, p, st);
+  if (h->trsm_l2_hints == 2) return launch_t<3, 2>(h, p, st);
+  if (h->trsm_l2_hints == 1) return launch_t<3, 1>(h, p, st);
+  return launch_t<3, 0>(h, p, st);
 }
 
 }  // namespace bopl
