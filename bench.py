@@ -216,9 +216,7 @@ def run_gpu(args):
     barrier()
     te = time.perf_counter()
     for _ in range(e2e_steps):
-        kind, th, th_d, wts, bst = acq._prepare(per_h=True)
-        _, v, i = eng.uei_host(Xh, acq.W_samples, kind, th, wts, bst.cpu().numpy(), 1, k=K_ANCHOR, index_offset=index_offset,
-                               want_acq=True, out=acq_h)
+        v, i, _ = acq.top_candidates(Xh, K_ANCHOR, index_offset, want_acq=True, out=acq_h)
         if world > 1:
             sharding.allgather_topk(v, i, Xh.numpy()[i - index_offset], K_ANCHOR, None, dev)
     barrier()
@@ -251,7 +249,7 @@ def run_gpu(args):
             "e2e": {"value": evals_per_step / float(e2e_t.item()), "unit": UNIT,
                     "h2d_bytes_per_step": int(N * d * 8 + (p["Z"].size + theta.size + 2 * len(theta)) * 8),
                     "d2h_bytes_per_step": int(N * 8 + K_ANCHOR * 16), "steps": e2e_steps,
-                    "api": "bopl_uei_host via uEI.top_candidates (pinned host candidates -> scores + top-20 on the host)"},
+                    "api": "uEI.top_candidates -> bopl_uei_host (pinned host candidates -> scores + top-20 on the host)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "posterior_trsm_t_kernel (fused K*, FP64 DMMA blocked triangular solve, mean, variance)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

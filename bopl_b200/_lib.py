@@ -24,7 +24,7 @@ VAR_CLIP = 2
 SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", "bopl_build_info", "bopl_set_model",
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
            "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
-           "bopl_uei_host", "bopl_launch_count"]
+           "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count"]
 
 
 class BoplError(RuntimeError):
@@ -98,6 +98,7 @@ def load():
     lib.bopl_topk.argtypes = [vp, dp, c_int, c_int, c_ll, dp, llp, vp]
     lib.bopl_uei_host.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, c_int, c_ll,
                                   dp, llp]
+    lib.bopl_uei_grad_host.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, dp]
     lib.bopl_launch_count.argtypes = [vp]
     lib.bopl_launch_count.restype = c_ll
     for name in SYMBOLS:

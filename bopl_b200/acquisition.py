@@ -133,33 +133,50 @@ class uEI(_UtilityAcquisition):
         """uEI.py:40-62 -> (N, 1)."""
         X = self._x(X)
         n_h = self.number_of_gp_hyps_samples
-        kind, theta, th_d, wts, best = self._prepare(per_h=(parallel and len(X) > 1))
-        acq = self.model.engine.uei_host(X, self.W_samples, kind, theta, wts, best.cpu().numpy(), n_h)
+        theta = self._thetas()
+        kind = self.utility.resolve_kind(self.n_attributes, theta[0])
+        best = self._incumbents_host(kind, theta, per_h=bool(parallel and len(X) > 1))
+        acq = self.model.engine.uei_host(X, self.W_samples, kind, theta, self._weights(len(theta)), best, n_h)
         self.model.set_hyperparameters(n_h - 1)
         return acq.reshape(X.shape[0], 1)
 
-    def top_candidates(self, X, k, index_offset=0, want_acq=False):
+    def top_candidates(self, X, k, index_offset=0, want_acq=False, out=None):
         """Batch value + the k best candidates in one call (what AnchorPointsGenerator.get does with argsort):
-        returns (values (k,), global indices (k,)[, acq (N,)])."""
-        X = self._x(X)
+        returns (values (k,), global indices (k,)[, acq (N,)]).  X may be a pinned torch CPU tensor (no staging copy);
+        `out` an optional (pinned) buffer for the scores."""
+        X = X if hasattr(X, "data_ptr") else self._x(X)
         n_h = self.number_of_gp_hyps_samples
-        kind, theta, th_d, wts, best = self._prepare(per_h=len(X) > 1)
-        acq, val, idx = self.model.engine.uei_host(X, self.W_samples, kind, theta, wts, best.cpu().numpy(), n_h, k=k,
-                                                   index_offset=index_offset, want_acq=want_acq)
+        theta = self._thetas()
+        kind = self.utility.resolve_kind(self.n_attributes, theta[0])
+        best = self._incumbents_host(kind, theta, per_h=len(X) > 1)
+        acq, val, idx = self.model.engine.uei_host(X, self.W_samples, kind, theta, self._weights(len(theta)), best, n_h, k=k,
+                                                   index_offset=index_offset, want_acq=want_acq, out=out)
         self.model.set_hyperparameters(n_h - 1)
         return (val, idx, acq) if want_acq else (val, idx)
+
+    def _incumbents_host(self, kind, theta, per_h):
+        """Host copy of the (n_h, L) incumbents, cached while theta, the model state and (for the stale variant) the
+        current hyper-sample stay the same — thousands of L-BFGS calls happen between two `update_samples`."""
+        key = (kind, per_h, None if per_h else self.model._h, self.number_of_gp_hyps_samples)
+        cache = self.__dict__.setdefault("_best_cache", {})
+        hit = cache.get(per_h)
+        if hit is not None and hit[0] == key and hit[1] is theta and hit[3] is self.model.state:
+            return hit[2]
+        th_d = self._dev("theta", theta) if theta is self.utility_parameter_samples else self.model.engine.to_dev(theta)
+        best = self._incumbents(kind, th_d, per_h).cpu().numpy()
+        cache[per_h] = (key, theta, best, self.model.state)
+        return best
 
     def _compute_acq_withGradients(self, X):
         """uEI.py:119-134 -> (N, 1), (N, d)."""
         X = self._x(X)
-        eng = self.model.engine
         n_h = self.number_of_gp_hyps_samples
-        kind, theta, th_d, wts, best = self._prepare(per_h=False)
-        w_src = self.utility_prob_dist if self.use_full_support else None
-        w_d = self._dev("wts", w_src) if w_src is not None and wts is w_src else self._dev_weights(wts)
-        acq, dacq = eng.uei_grad_dev(eng.to_dev(X), self._dev("Z", self.W_samples), kind, th_d, w_d, best, n_h)
+        theta = self._thetas()
+        kind = self.utility.resolve_kind(self.n_attributes, theta[0])
+        best = self._incumbents_host(kind, theta, per_h=False)
+        acq, dacq = self.model.engine.uei_grad_host(X, self.W_samples, kind, theta, self._weights(len(theta)), best, n_h)
         self.model.set_hyperparameters(n_h - 1)
-        return acq.cpu().numpy().reshape(X.shape[0], 1), dacq.cpu().numpy().reshape(X.shape)
+        return acq.reshape(X.shape[0], 1), dacq.reshape(X.shape)
 
     def update_samples(self):                                            # uEI.py:170-177
         self.W_samples = np.random.normal(size=self.W_samples.shape)

@@ -186,7 +186,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -442,6 +442,49 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
                                  best + (size_t)hh * Lt, scale, hh > 0, acq, dacq, st)))
       return rc;
   }
+  return BOPL_OK;
+}
+
+int bopl_uei_grad_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, int nw, int util_kind,
+                       const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
+                       double* acq_h, double* dacq_h) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  int rc = check_utility(h, util_kind, Lt, p);
+  if (rc) return rc;
+  if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
+  if (N == 0) return BOPL_OK;
+  if (!Xc_h || !Z_h || !theta_h || !wts_h || !best_h || !acq_h || !dacq_h) return fail(h, BOPL_ERR_INVALID, "null buffer");
+  if (!h->has_winv) return fail(h, BOPL_ERR_STATE, "gradients need Winv (bopl_set_model was given NULL)");
+  const int d = h->d;
+  const size_t nX = (size_t)N * d, nZ = (size_t)nw * h->m, nT = (size_t)Lt * p, nB = (size_t)nH * Lt;
+  const size_t total = nX + nZ + nT + Lt + nB + N + nX;     // X | Z | theta | wts | best | acq | dacq
+  if ((rc = ensure_bytes(h, (void**)&h->gh_dev, &h->gh_cap, total * sizeof(double)))) return rc;
+  double* Xd = h->gh_dev;
+  double* Zd = Xd + nX;
+  double* thd = Zd + nZ;
+  double* wd = thd + nT;
+  double* bd = wd + Lt;
+  double* ad = bd + nB;
+  double* gd = ad + N;
+  cudaStream_t st = h->s_compute;
+  BOPL_CUDA(h, cudaMemcpyAsync(Xd, Xc_h, nX * sizeof(double), cudaMemcpyHostToDevice, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(Zd, Z_h, nZ * sizeof(double), cudaMemcpyHostToDevice, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(thd, theta_h, nT * sizeof(double), cudaMemcpyHostToDevice, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(wd, wts_h, (size_t)Lt * sizeof(double), cudaMemcpyHostToDevice, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(bd, best_h, nB * sizeof(double), cudaMemcpyHostToDevice, st));
+  if ((rc = ensure_mv(h, (size_t)h->m * N)) || (rc = ensure_grad(h, (size_t)h->m * N * d))) return rc;
+  const double scale = 1.0 / ((double)nH * (double)nw);
+  for (int hh = 0; hh < nH; ++hh) {
+    if ((rc = launch_posterior_trsm(h, Xd, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
+    if ((rc = launch_posterior_grad(h, Xd, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
+    if ((rc = launch_uei_mc_grad(h, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, N, Zd, nw, util_kind, thd, Lt, p, wd,
+                                 bd + (size_t)hh * Lt, scale, hh > 0, ad, gd, st)))
+      return rc;
+  }
+  BOPL_CUDA(h, cudaMemcpyAsync(acq_h, ad, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(dacq_h, gd, nX * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOPL_CUDA(h, cudaStreamSynchronize(st));
   return BOPL_OK;
 }
 

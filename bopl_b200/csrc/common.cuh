@@ -75,6 +75,7 @@ struct bopl_handle {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   double* hx_dev = nullptr; size_t hx_cap = 0;       // [2][chunk*d] candidate double buffer
   double* hacq_dev = nullptr; size_t hacq_cap = 0;   // [N]
+  double* gh_dev = nullptr; size_t gh_cap = 0;       // staging of the host-buffer value+gradient call
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
   size_t hsmall_cap = 0;
 };

@@ -215,6 +215,19 @@ class Engine(object):
                                        self._stream()))
         return val, idx
 
+    def uei_grad_host(self, Xc, Z, kind, theta, wts, best, nH):
+        """NumPy in / NumPy out value + gradient through `bopl_uei_grad_host` (one library call, one synchronisation)."""
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        Xc, Z, theta, wts, best = c(Xc), c(Z), c(theta), c(wts), c(best)
+        N = Xc.shape[0]
+        Lt, p = theta.shape
+        acq = np.empty(N)
+        dacq = np.empty((N, self.d))
+        ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self._check(self.lib.bopl_uei_grad_host(self.h, ptr(Xc), N, ptr(Z), Z.shape[0], UTILITY_KINDS[kind], ptr(theta), Lt, p,
+                                                ptr(wts), ptr(best), nH, ptr(acq), ptr(dacq)))
+        return acq, dacq
+
     # ------------------------------------------------------------------ host-buffer path (the reference-facing call)
     def uei_host(self, Xc, Z, kind, theta, wts, best, nH, k=0, index_offset=0, want_acq=True, out=None):
         """NumPy in / NumPy out through `bopl_uei_host` (chunked H2D overlapped with compute inside the library).

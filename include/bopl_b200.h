@@ -169,6 +169,13 @@ int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, 
                   const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
                   double* acq_h, int k, long long index_offset, double* topk_val_h, long long* topk_idx_h);
 
+/* Host-buffer value + gradient (the call shape of the L-BFGS inner loop, optimization_services/acquisition_optimizer.py:112 ->
+ * GPyOpt/optimization/optimizer.py:182: one point, or one point per anchor in the lock-step driver): bopl_uei_grad with HOST
+ * buffers, copies inside, one synchronisation.  acq_h [N], dacq_h [N*d]. */
+int bopl_uei_grad_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, int nw, int util_kind,
+                       const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
+                       double* acq_h, double* dacq_h);
+
 /* Number of kernel launches issued through this handle since creation (bench.py reports the delta). */
 long long bopl_launch_count(const bopl_handle* h);
 
