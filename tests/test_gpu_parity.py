@@ -555,3 +555,33 @@ def test_bo_loop_end_to_end_with_host_fit():
     assert X.shape == (14 + 3, 6) and Y.shape == (2, 17)
     assert np.all(X >= 0.0) and np.all(X <= 1.0) and np.all(np.isfinite(Y))
     assert all(b >= a for a, b in zip(hist, hist[1:]))
+
+
+def test_mixed_kernels_per_attribute_and_non_ard():
+    """Different GPy kernels per attribute in one model, one of them non-ARD (a single lengthscale: the reference then
+    divides the distance, stationary.py:163-166, the library the inputs — same number up to rounding)."""
+    from oracle.gp import ExactGP, MultiOutputGPOracle
+    from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
+    rs = np.random.RandomState(5)
+    n, N, d = 90, 200, 4
+    kinds = ["Mat52", "rbf", "Mat32", "ExpQuad"]
+    m = len(kinds)
+    X = rs.uniform(size=(n, d))
+    Y = np.stack([np.cos(3 * X @ rs.normal(size=d)) for _ in range(m)])
+    ell = rs.uniform(0.4, 0.9, size=(m, 1, d))
+    ell[1] = ell[1, 0, 0]                                   # attribute 1: one lengthscale for every input (non-ARD)
+    var = rs.uniform(0.5, 2.0, size=(m, 1))
+    noise = np.full((m, 1), 1e-3)
+    Xc = rs.uniform(size=(N, d))
+    gps = [[ExactGP(X, Y[j], kinds[j], var[j, 0], ell[j, 0] if j != 1 else ell[1, 0, :1], noise[j, 0], ARD=(j != 1))]
+           for j in range(m)]
+    om = MultiOutputGPOracle(gps)
+    gm = MultiOutputGP.from_state(state_from_hyperparameters(X, Y, kinds, var, ell, noise))
+    mu_o, v_o = om.predict(Xc)
+    mu_g, v_g = gm.predict(Xc)
+    check_close(mu_g, mu_o, "mixed kernels mean")
+    floor = variance_floor(om, Xc)
+    assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor)
+    check_close(gm.posterior_mean_gradient(Xc[:50]), om.posterior_mean_gradient(Xc[:50]), "mixed kernels dmean")
+    check_dvar(gm.posterior_variance_gradient(Xc[:50]), om, Xc[:50], "mixed kernels dvar")
+    check_close(gm.predict(Xc[:7])[1], om.predict(Xc[:7])[1], "small path var", rtol=1e-8)
