@@ -96,7 +96,7 @@ def run_reference(args):
         return
     w = workload(args)
     n_sample = args.cpu_sample
-    p = make_problem("S", n=w["n"], N=n_sample, n_w=w["n_w"], L=w["L"])
+    p = make_problem("S", n=w["n"], N=n_sample, n_w=w["n_w"], L=w["L"], utility=args.utility)
     value, t = cpu_oracle_run(p, n_sample, max(1, args.steps), args.warmup)
     cores = os.cpu_count()
     sample = "%d of the %d candidates per step (n=%d, m=3, n_w=%d, L=%d)" % (n_sample, w["N"], w["n"], w["n_w"], w["L"])
@@ -104,7 +104,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "S: d=10 m=3 n=%d N=%d n_w=%d L=%d H=1 Matern52-ARD linear utility" % (w["n"], w["N"], w["n_w"], w["L"])},
+        "config": {"workload": "S: d=10 m=3 n=%d N=%d n_w=%d L=%d H=1 Matern52-ARD %s utility" % (w["n"], w["N"], w["n_w"], w["L"], args.utility)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -139,7 +139,7 @@ def run_gpu(args):
 
     w = workload(args)
     N = w["N"]
-    p = make_problem("S", n=w["n"], N=16, n_w=w["n_w"], L=w["L"])
+    p = make_problem("S", n=w["n"], N=16, n_w=w["n_w"], L=w["L"], utility=args.utility)
     d, m = p["d"], p["m"]
     state = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"], want_winv=False,
                                        want_linv=False)
@@ -148,7 +148,7 @@ def run_gpu(args):
     theta = p["theta"]
     udist = UtilityDistribution(support=theta, prob_dist=np.ones(len(theta)) / len(theta), use_full_support=False,
                                 prior_sample_generator=lambda k, seed=None: theta[:k])
-    util = Utility(func=lambda y, t: np.dot(t, y), parameter_distribution=udist, kind="linear")
+    util = Utility(func=None, parameter_distribution=udist, kind=args.utility)
     acq = uEI(model, BoxSpace([(0.0, 1.0)] * d), utility=util)
     acq.W_samples = p["Z"]
     acq.utility_parameter_samples = theta
@@ -163,7 +163,7 @@ def run_gpu(args):
     Xd = Xh.to(dev)
     Zd, thd = eng.to_dev(p["Z"]), eng.to_dev(theta)
     wd = eng.to_dev(np.full(len(theta), 1.0 / len(theta)))
-    best = eng.incumbent_dev("linear", thd)[:1].contiguous()
+    best = eng.incumbent_dev(args.utility, thd)[:1].contiguous()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     scale = 1.0 / w["n_w"]
     trsm_ms = []
@@ -177,7 +177,7 @@ def run_gpu(args):
         if timed:
             e1.record()
             trsm_ms.append((e0, e1))
-        a = eng.uei_mc_dev(mean, var, Zd, "linear", thd, wd, best, scale)      # kernel (3)
+        a = eng.uei_mc_dev(mean, var, Zd, args.utility, thd, wd, best, scale)  # kernel (3)
         val, idx = eng.topk_dev(a, K_ANCHOR, index_offset)
         if world > 1:
             idx_c = idx.cpu().numpy()
@@ -241,8 +241,8 @@ def run_gpu(args):
             "metric": METRIC, "value": evals_per_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "S: d=10 m=3 n=%d N=%d candidates per GPU, n_w=%d L=%d H=1 Matern52-ARD noise=1e-6 linear utility, top-%d anchors"
-                                   % (w["n"], N, w["n_w"], w["L"], K_ANCHOR),
+            "config": {"workload": "S: d=10 m=3 n=%d N=%d candidates per GPU, n_w=%d L=%d H=1 Matern52-ARD noise=1e-6 %s utility, top-%d anchors"
+                                   % (w["n"], N, w["n_w"], w["L"], args.utility, K_ANCHOR),
                        "sharding": "candidates row-sharded, %d per rank; all-gather of top-%d records only" % (N, K_ANCHOR),
                        "l2": "working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2, and a 256 MB flush write between steps"},
             "clocks": sampler.summary(),
@@ -258,7 +258,7 @@ def run_gpu(args):
                                         "(MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.0)"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            pc = make_problem("S", n=w["n"], N=args.cpu_sample, n_w=w["n_w"], L=w["L"])
+            pc = make_problem("S", n=w["n"], N=args.cpu_sample, n_w=w["n_w"], L=w["L"], utility=args.utility)
             v, t = cpu_oracle_run(pc, args.cpu_sample, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                    "sample": "%d of the %d candidates, one pass of the NumPy/SciPy (LAPACK dtrtrs) restatement, %.1f s"
@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--n", type=int, default=2000)
     ap.add_argument("--n_w", type=int, default=64)
     ap.add_argument("--L", type=int, default=32)
+    ap.add_argument("--utility", default="linear", choices=["linear", "quadratic", "exponential"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
