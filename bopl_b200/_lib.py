@@ -35,12 +35,24 @@ class BoplError(RuntimeError):
         self.code = code
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash():
+    """Content hash of every source, header and flag the library is built from (mtimes do not survive a repo snapshot)."""
+    import hashlib
+    hh = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, x)) for x in HEADERS]:
+        with open(path, "rb") as f:
+            hh.update(path.encode() + b"\0" + f.read())
+    return hh.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, hh)) for hh in HEADERS]
-    return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -57,6 +69,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout)
     if verbose:
         print(res.stdout)
+    with open(HASH_PATH, "w") as f:
+        f.write(_source_hash())
     return LIB_PATH
 
 
