@@ -10,21 +10,23 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
-SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu"]
+SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0"]
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}
 VAR_INCLUDE_NOISE = 1
 VAR_CLIP = 2
+ERR_NUMERIC = -5
 
 # every symbol include/bopl_b200.h declares
 SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", "bopl_build_info", "bopl_set_model",
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
            "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
-           "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count"]
+           "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count", "bopl_fit_model", "bopl_log_marginal",
+           "bopl_get_factor"]
 
 
 class BoplError(RuntimeError):
@@ -97,6 +99,9 @@ def load():
     lib.bopl_build_info.argtypes = []
     lib.bopl_build_info.restype = ctypes.c_char_p
     lib.bopl_set_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.bopl_fit_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, c_int, c_int, dp]
+    lib.bopl_log_marginal.argtypes = [vp, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, ip]
+    lib.bopl_get_factor.argtypes = [vp, c_int, c_int, dp, dp, dp, dp]
     lib.bopl_cross_cov.argtypes = [vp, dp, c_int, c_int, c_int, dp, vp]
     lib.bopl_posterior.argtypes = [vp, dp, c_int, c_int, dp, dp, c_int, vp]
     lib.bopl_posterior_mean.argtypes = [vp, dp, c_int, c_int, dp, vp]

@@ -2,6 +2,7 @@
 // that sequence the kernels.  Plain pointers and sizes only; every entry returns a bopl_status.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <thread>
 #include <cstdlib>
@@ -30,8 +31,6 @@ int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes) {
   return BOPL_OK;
 }
 
-namespace {
-
 void free_model(bopl_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear();
@@ -43,6 +42,8 @@ void free_model(bopl_handle* h) {
   h->has_linv = false;
   h->F_valid = false;
 }
+
+namespace {
 
 template <typename T>
 int dev_upload(bopl_handle* h, const T* src, size_t count, T** out) {
@@ -73,17 +74,6 @@ bool invert_lower_block(const double* D, int ld, int B, double* out) {
   for (size_t i = 0; i < (size_t)B * B; ++i) out[i] = (double)x[i];
   return true;
 }
-
-#define BOPL_CHECK_HANDLE(h)                                             \
-  do {                                                                   \
-    if (!(h)) return bopl::fail(nullptr, BOPL_ERR_INVALID, "null handle"); \
-    BOPL_CUDA((h), cudaSetDevice((h)->device));                           \
-  } while (0)
-
-#define BOPL_NEED_MODEL(h)                                                                        \
-  do {                                                                                            \
-    if (!(h)->has_model) return bopl::fail((h), BOPL_ERR_STATE, "bopl_set_model has not been called"); \
-  } while (0)
 
 int check_utility(bopl_handle* h, int util_kind, int Lt, int p) {
   if (Lt <= 0) return fail(h, BOPL_ERR_INVALID, "Lt must be positive");
@@ -186,7 +176,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev, h->fit_ws};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -623,6 +613,252 @@ int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, 
     BOPL_CUDA(h, cudaMemcpyAsync(topk_idx_h, tki, (size_t)k * sizeof(long long), cudaMemcpyDeviceToHost, sc));
   }
   BOPL_CUDA(h, cudaStreamSynchronize(sc));
+  return BOPL_OK;
+}
+
+// ---- model fit on the device (fit_kernels.cu) ---------------------------------------------------------------------------
+int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
+                   const double* jitter_h, int want_winv, int want_linv, double* logdet_h) {
+  BOPL_CHECK_HANDLE(h);
+  if (n <= 0 || d <= 0 || m <= 0 || H <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, m, H must be positive");
+  if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
+  if (m > MAX_M) return fail(h, BOPL_ERR_UNSUPPORTED, "m > 16 attributes");
+  if (!kern_kind_h || !X_h || !Y_h || !ell_h || !var_h || !noise_h) return fail(h, BOPL_ERR_INVALID, "null model array");
+  const int G = m * H;
+  for (int i = 0; i < G; ++i) {
+    if (kern_kind_h[i] < BOPL_KERN_MAT52 || kern_kind_h[i] > BOPL_KERN_EXPQUAD) return fail(h, BOPL_ERR_INVALID, "unknown kernel kind");
+    if (!(var_h[i] > 0.0) || !(noise_h[i] >= 0.0)) return fail(h, BOPL_ERR_INVALID, "kernel variance must be > 0 and noise >= 0");
+    if (jitter_h && !(jitter_h[i] >= 0.0)) return fail(h, BOPL_ERR_INVALID, "jitter must be >= 0");
+    for (int q = 0; q < d; ++q)
+      if (!(ell_h[(size_t)i * d + q] > 0.0)) return fail(h, BOPL_ERR_INVALID, "lengthscales must be > 0");
+  }
+  BOPL_CUDA(h, cudaDeviceSynchronize());
+  const bool timing = getenv("BOPL_FIT_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  free_model(h);
+  const double t1 = now();
+  h->n = n;
+  h->d = d;
+  h->m = m;
+  h->H = H;
+  h->n_pad = ((n + TRSM_BM - 1) / TRSM_BM) * TRSM_BM;
+  h->pad = h->n_pad - n;
+  const int n_pad = h->n_pad, nblk = n_pad / TRSM_BM;
+  const bool inverse = want_winv || want_linv;
+  int rc;
+  if ((rc = dev_upload(h, X_h, (size_t)n * d, &h->X_dev))) return rc;
+  // centred targets per attribute (this fork's normaliser subtracts the mean only: util/normalizer.py:57-72)
+  std::vector<double> yc((size_t)m * n), ymean(m);
+  for (int j = 0; j < m; ++j) {
+    long double s = 0.0L;
+    for (int i = 0; i < n; ++i) s += Y_h[(size_t)j * n + i];
+    ymean[j] = (double)(s / n);
+    for (int i = 0; i < n; ++i) yc[(size_t)j * n + i] = Y_h[(size_t)j * n + i] - ymean[j];
+  }
+  double *yc_dev, *logdiag_dev, *quad_dev;
+  int* info_dev;
+  if ((rc = dev_upload(h, yc.data(), yc.size(), &yc_dev))) { free_model(h); return rc; }
+  std::vector<double> zeros((size_t)G * nblk + G, 0.0);
+  std::vector<int> izeros(G, 0);
+  if ((rc = dev_upload(h, zeros.data(), (size_t)G * nblk, &logdiag_dev)) || (rc = dev_upload(h, zeros.data(), (size_t)G, &quad_dev)) ||
+      (rc = dev_upload(h, izeros.data(), (size_t)G, &info_dev))) { free_model(h); return rc; }
+  const size_t fsz = fit_dev_struct_bytes();
+  std::vector<char> fits((size_t)G * fsz);
+  std::vector<double*> Us;
+  h->gp_host.resize((size_t)G);
+  auto dalloc = [&](size_t count, double** out, bool owned) -> int {
+    void* p = nullptr;
+    BOPL_CUDA(h, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(double)));
+    if (owned) h->owned.push_back(p);
+    *out = (double*)p;
+    return BOPL_OK;
+  };
+  auto cleanup = [&]() {
+    for (double* u : Us) cudaFree(u);
+    Us.clear();
+  };
+  for (int g = 0; g < G; ++g) {
+    double *pL, *pD, *pF, *pS, *pX, *pa, *pe, *pW = nullptr, *pLi = nullptr, *pU = nullptr;
+    if ((rc = dalloc((size_t)n_pad * n_pad, &pL, true)) || (rc = dalloc((size_t)nblk * TRSM_BM * TRSM_BM, &pD, true)) ||
+        (rc = dalloc((size_t)nblk * 136 * 64, &pF, true)) || (rc = dalloc((size_t)n_pad * (d + 1), &pS, true)) ||
+        (rc = dalloc((size_t)n_pad * d, &pX, true)) || (rc = dalloc((size_t)n_pad, &pa, true)) ||
+        (rc = dev_upload(h, ell_h + (size_t)g * d, (size_t)d, &pe)) ||
+        (want_winv && (rc = dalloc((size_t)n * n, &pW, true))) || (want_linv && (rc = dalloc((size_t)n * n, &pLi, true))) ||
+        (inverse && (rc = dalloc((size_t)n_pad * n_pad, &pU, false)))) {
+      cleanup();
+      free_model(h);
+      return rc;
+    }
+    if (pU) Us.push_back(pU);
+    cudaMemsetAsync(pL, 0, (size_t)n_pad * n_pad * sizeof(double), h->s_compute);
+    const double diag_add = noise_h[g] + 1e-8 + (jitter_h ? jitter_h[g] : 0.0);   // exact_gaussian_inference.py:46
+    fit_dev_fill(fits.data() + (size_t)g * fsz, pL, pD, pF, pU, pW, pLi, pX, pa, pS, pe, yc_dev + (size_t)(g / H) * n,
+                 logdiag_dev + (size_t)g * nblk, quad_dev + g, info_dev + g, var_h[g], diag_add, kern_kind_h[g]);
+    GpDev gp{};
+    gp.Linv = pLi;
+    gp.Lneg = pL;
+    gp.Dinv = pD;
+    gp.DinvFrag = pF;
+    gp.StageBlk = pS;
+    gp.Xs = pX;
+    gp.alpha = pa;
+    gp.ell = pe;
+    gp.Winv = pW;
+    gp.variance = var_h[g];
+    gp.noise = noise_h[g];
+    gp.ymean = ymean[g / H];
+    gp.kind = kern_kind_h[g];
+    h->gp_host[g] = gp;
+  }
+  char* fits_dev;
+  const double t2 = now();
+  if ((rc = dev_upload(h, fits.data(), fits.size(), &fits_dev)) ||
+      (rc = fit_factorize(h, fits_dev, G, h->X_dev, n, d, inverse, want_winv != 0, want_linv != 0, h->s_compute))) {
+    cleanup();
+    free_model(h);
+    return rc;
+  }
+  cudaError_t e = cudaStreamSynchronize(h->s_compute);
+  const double t3 = now();
+  cleanup();
+  if (timing)
+    fprintf(stderr, "bopl_fit_model: free %.2f ms, alloc %.2f ms, kernels %.2f ms, scratch free %.2f ms\n", t1 - t0, t2 - t1, t3 - t2,
+            now() - t3);
+  if (e != cudaSuccess) {
+    free_model(h);
+    return fail(h, BOPL_ERR_CUDA, std::string("device fit: ") + cudaGetErrorString(e));
+  }
+  std::vector<int> info(G);
+  std::vector<double> logdiag((size_t)G * nblk);
+  BOPL_CUDA(h, cudaMemcpy(info.data(), info_dev, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
+  BOPL_CUDA(h, cudaMemcpy(logdiag.data(), logdiag_dev, logdiag.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int g = 0; g < G; ++g)
+    if (info[g]) {
+      free_model(h);
+      return fail(h, BOPL_ERR_NUMERIC, "covariance matrix of attribute " + std::to_string(g / H) + ", hyper-sample " +
+                                           std::to_string(g % H) + " is not positive definite (pivot " +
+                                           std::to_string(info[g] - 1 - h->pad) + ")");
+    }
+  if (logdet_h)
+    for (int g = 0; g < G; ++g) {
+      double s = 0.0;
+      for (int b = 0; b < nblk; ++b) s += logdiag[(size_t)g * nblk + b];
+      logdet_h[g] = 2.0 * s;
+    }
+  GpDev* gd;
+  if ((rc = dev_upload(h, h->gp_host.data(), h->gp_host.size(), &gd))) {
+    free_model(h);
+    return rc;
+  }
+  h->gp_dev = gd;
+  h->has_winv = want_winv != 0;
+  h->has_linv = want_linv != 0;
+  h->has_model = true;
+  h->F_valid = false;
+  return BOPL_OK;
+}
+
+int bopl_log_marginal(bopl_handle* h, int n, int d, int G, const int* kern_kind_h, const double* X_h, const double* Yc_h,
+                      const double* ell_h, const double* var_h, const double* noise_h, double* ll_h, double* grad_h,
+                      int* info_h) {
+  BOPL_CHECK_HANDLE(h);
+  if (n <= 0 || d <= 0 || G <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, G must be positive");
+  if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
+  if (!kern_kind_h || !X_h || !Yc_h || !ell_h || !var_h || !noise_h || !ll_h || !info_h) return fail(h, BOPL_ERR_INVALID, "null array");
+  for (int i = 0; i < G; ++i) {
+    if (kern_kind_h[i] < BOPL_KERN_MAT52 || kern_kind_h[i] > BOPL_KERN_EXPQUAD) return fail(h, BOPL_ERR_INVALID, "unknown kernel kind");
+    if (!(var_h[i] > 0.0) || !(noise_h[i] >= 0.0)) return fail(h, BOPL_ERR_INVALID, "kernel variance must be > 0 and noise >= 0");
+    for (int q = 0; q < d; ++q)
+      if (!(ell_h[(size_t)i * d + q] > 0.0)) return fail(h, BOPL_ERR_INVALID, "lengthscales must be > 0");
+  }
+  const int n_pad = ((n + TRSM_BM - 1) / TRSM_BM) * TRSM_BM, nblk = n_pad / TRSM_BM, nstrips = (n + 31) / 32;
+  const bool grad = grad_h != nullptr;
+  const size_t fsz = fit_dev_struct_bytes();
+  // carve one slab: per instance A, Dinv, DinvFrag, Xs, alpha, ell, y (+ U, Winv for the gradient), then the shared pieces
+  auto al = [](size_t x) { return (x + 31) & ~(size_t)31; };
+  const size_t cA = al((size_t)n_pad * n_pad), cD = al((size_t)nblk * TRSM_BM * TRSM_BM), cF = al((size_t)nblk * 136 * 64),
+               cX = al((size_t)n_pad * d), ca = al((size_t)n_pad), ce = al((size_t)d), cy = al((size_t)n), cW = al((size_t)n * n);
+  const size_t per = cA + cD + cF + cX + ca + ce + cy + (grad ? cA + cW : 0);
+  const size_t shared = al((size_t)n * d) + al((size_t)G * nblk) + al((size_t)G) + al((size_t)G) /*info as doubles' space*/ +
+                        al((size_t)G * nstrips * (d + 2)) + al((size_t)G * (d + 2)) + al((G * fsz + 7) / 8);
+  int rc;
+  if ((rc = ensure_bytes(h, &h->fit_ws, &h->fit_ws_bytes, (per * G + shared) * sizeof(double)))) return rc;
+  double* base = (double*)h->fit_ws;
+  double* sh = base + per * G;
+  double* X_dev = sh;                      sh += al((size_t)n * d);
+  double* logdiag_dev = sh;                sh += al((size_t)G * nblk);
+  double* quad_dev = sh;                   sh += al((size_t)G);
+  int* info_dev = (int*)sh;                sh += al((size_t)G);
+  double* partial_dev = sh;                sh += al((size_t)G * nstrips * (d + 2));
+  double* out_dev = sh;                    sh += al((size_t)G * (d + 2));
+  char* fits_dev = (char*)sh;
+  cudaStream_t st = h->s_compute;
+  std::vector<char> fits((size_t)G * fsz);
+  for (int g = 0; g < G; ++g) {
+    double* p = base + per * g;
+    double* A = p;      p += cA;
+    double* D = p;      p += cD;
+    double* F = p;      p += cF;
+    double* Xs = p;     p += cX;
+    double* a = p;      p += ca;
+    double* e = p;      p += ce;
+    double* y = p;      p += cy;
+    double *U = nullptr, *W = nullptr;
+    if (grad) {
+      U = p;  p += cA;
+      W = p;
+    }
+    BOPL_CUDA(h, cudaMemcpyAsync(e, ell_h + (size_t)g * d, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, st));
+    BOPL_CUDA(h, cudaMemcpyAsync(y, Yc_h + (size_t)g * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    fit_dev_fill(fits.data() + (size_t)g * fsz, A, D, F, U, W, nullptr, Xs, a, nullptr, e, y, logdiag_dev + (size_t)g * nblk,
+                 quad_dev + g, info_dev + g, var_h[g], noise_h[g] + 1e-8, kern_kind_h[g]);
+  }
+  BOPL_CUDA(h, cudaMemcpyAsync(X_dev, X_h, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(fits_dev, fits.data(), fits.size(), cudaMemcpyHostToDevice, st));
+  if ((rc = fit_factorize(h, fits_dev, G, X_dev, n, d, grad, grad, false, st))) return rc;
+  if (grad && (rc = fit_lml_grad(h, fits_dev, G, n, d, partial_dev, out_dev, st))) return rc;
+  std::vector<double> logdiag((size_t)G * nblk), quad(G);
+  BOPL_CUDA(h, cudaMemcpyAsync(logdiag.data(), logdiag_dev, logdiag.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(quad.data(), quad_dev, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOPL_CUDA(h, cudaMemcpyAsync(info_h, info_dev, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (grad) BOPL_CUDA(h, cudaMemcpyAsync(grad_h, out_dev, (size_t)G * (d + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOPL_CUDA(h, cudaStreamSynchronize(st));
+  for (int g = 0; g < G; ++g) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += logdiag[(size_t)g * nblk + b];
+    // exact_gaussian_inference.py:51: 0.5 (-n log 2pi - log|K| - y^T alpha)
+    ll_h[g] = 0.5 * (-(double)n * 1.8378770664093454836 - 2.0 * s - quad[g]);
+  }
+  return BOPL_OK;
+}
+
+int bopl_get_factor(bopl_handle* h, int j, int hsel, double* L_h, double* alpha_h, double* Winv_h, double* Linv_h) {
+  BOPL_CHECK_HANDLE(h);
+  BOPL_NEED_MODEL(h);
+  if (j < 0 || j >= h->m || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad j / hsel");
+  if (Winv_h && !h->has_winv) return fail(h, BOPL_ERR_STATE, "Winv was not loaded");
+  if (Linv_h && !h->has_linv) return fail(h, BOPL_ERR_STATE, "Linv was not loaded");
+  BOPL_CUDA(h, cudaDeviceSynchronize());
+  const GpDev& gp = h->gp_host[(size_t)j * h->H + hsel];
+  const int n = h->n, n_pad = h->n_pad, pad = h->pad;
+  if (L_h) {
+    std::vector<double> Lp((size_t)n_pad * n_pad);
+    BOPL_CUDA(h, cudaMemcpy(Lp.data(), gp.Lneg, Lp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      const int R = pad + i, bi = R / TRSM_BM;
+      for (int k = 0; k < n; ++k) {
+        const int C = pad + k;
+        double v = (k <= i) ? Lp[(size_t)R * n_pad + C] : 0.0;
+        if (k <= i && C / TRSM_BM < bi) v = -v;      // off-diagonal blocks are stored negated
+        L_h[(size_t)i * n + k] = v;
+      }
+    }
+  }
+  if (alpha_h) BOPL_CUDA(h, cudaMemcpy(alpha_h, gp.alpha + pad, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Winv_h) BOPL_CUDA(h, cudaMemcpy(Winv_h, gp.Winv, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Linv_h) BOPL_CUDA(h, cudaMemcpy(Linv_h, gp.Linv, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
   return BOPL_OK;
 }
 

@@ -76,6 +76,7 @@ struct bopl_handle {
   double* hx_dev = nullptr; size_t hx_cap = 0;       // [2][chunk*d] candidate double buffer
   double* hacq_dev = nullptr; size_t hacq_cap = 0;   // [N]
   double* gh_dev = nullptr; size_t gh_cap = 0;       // staging of the host-buffer value+gradient call
+  void* fit_ws = nullptr; size_t fit_ws_bytes = 0;   // workspace of bopl_log_marginal (factor, inverse, K^-1 of every instance)
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
   size_t hsmall_cap = 0;
 };
@@ -101,7 +102,28 @@ int fail(bopl_handle* h, int code, const std::string& msg);
     (h)->launches++;                                                                              \
   } while (0)
 
+#define BOPL_CHECK_HANDLE(h)                                             \
+  do {                                                                   \
+    if (!(h)) return bopl::fail(nullptr, BOPL_ERR_INVALID, "null handle"); \
+    BOPL_CUDA((h), cudaSetDevice((h)->device));                           \
+  } while (0)
+
+#define BOPL_NEED_MODEL(h)                                                                        \
+  do {                                                                                            \
+    if (!(h)->has_model) return bopl::fail((h), BOPL_ERR_STATE, "bopl_set_model has not been called"); \
+  } while (0)
+
 int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes);
+void free_model(bopl_handle* h);
+
+// device-side model fit (fit_kernels.cu); FitDev is private to that translation unit
+size_t fit_dev_struct_bytes();
+void fit_dev_fill(void* slot, double* A, double* Dinv, double* DinvFrag, double* U, double* Winv, double* Linv, double* Xs,
+                  double* alpha, double* StageBlk, double* ell, const double* y, double* logdiag, double* quad, int* info,
+                  double variance, double diag_add, int kind);
+int fit_factorize(bopl_handle* h, const void* fits_dev, int G, const double* X_dev, int n, int d, bool want_inverse,
+                  bool want_winv, bool want_linv, cudaStream_t st);
+int fit_lml_grad(bopl_handle* h, const void* fits_dev, int G, int n, int d, double* partial, double* out, cudaStream_t st);
 
 // launchers implemented in the kernel translation units
 int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,

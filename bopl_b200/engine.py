@@ -29,8 +29,10 @@ class GPState(object):
         self.lengthscale = np.ascontiguousarray(lengthscale, dtype=np.float64).reshape(self.m, self.H, self.d)
         self.noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(self.m, self.H)
         self.ymean = np.ascontiguousarray(ymean, dtype=np.float64).reshape(self.m, self.H)
-        self.L = np.ascontiguousarray(L, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
-        self.alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(self.m, self.H, self.n)
+        # L / alpha are None for a state fitted on the device (Engine.fit_model): the factor never existed on the host
+        self.L = None if L is None else np.ascontiguousarray(L, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
+        self.alpha = None if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64).reshape(self.m, self.H, self.n)
+        self.on_device = False
         self.Winv = None if Winv is None else \
             np.ascontiguousarray(Winv, dtype=np.float64).reshape(self.m, self.H, self.n, self.n)
         self.Linv = None if Linv is None else \
@@ -92,6 +94,8 @@ class Engine(object):
 
     # ------------------------------------------------------------------ model
     def set_model(self, state):
+        if state.L is None:
+            raise BoplError(-3, "this GPState was fitted on the device (Engine.fit_model) and holds no host factor to upload")
         kinds = np.ascontiguousarray([[KERNEL_KINDS[str(k)] for k in row] for row in state.kinds], dtype=np.int32)
         p = lambda a: ctypes.c_void_p(a.ctypes.data)
         self._check(self.lib.bopl_set_model(
@@ -101,6 +105,77 @@ class Engine(object):
             p(state.Linv) if state.Linv is not None else None))
         self.state = state
         self.n, self.d, self.m, self.H = state.n, state.d, state.m, state.H
+
+    def fit_model(self, X, Y, kinds, variance, lengthscale, noise, want_winv=True, want_linv=True, max_tries=10):
+        """Fit every (attribute, hyper-sample) posterior ON THE DEVICE (`bopl_fit_model`): K, blocked Cholesky, alpha,
+        K^-1, L^-1 — nothing but X, Y and the hyper-parameters crosses the bus.  A matrix that is not positive definite
+        is retried with growing diagonal jitter exactly as `GPy/util/linalg.py:53-78` (jitchol) does.
+        Returns a `GPState` without the factor arrays (read them back with `get_factor` if needed)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n, d = X.shape
+        variance = np.ascontiguousarray(variance, dtype=np.float64)
+        m, H = variance.shape
+        lengthscale = np.asarray(lengthscale, dtype=np.float64).reshape(m, H, -1)
+        if lengthscale.shape[2] == 1 and d > 1:
+            lengthscale = np.repeat(lengthscale, d, axis=2)
+        lengthscale = np.ascontiguousarray(lengthscale)
+        noise = np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(m, H))
+        kinds = np.asarray(kinds)
+        kinds = np.repeat(kinds.reshape(m, 1), H, axis=1) if kinds.size == m else kinds.reshape(m, H)
+        kind_ids = np.ascontiguousarray([[KERNEL_KINDS[str(k)] for k in row] for row in kinds], dtype=np.int32)
+        Ym = np.ascontiguousarray(np.stack([np.asarray(Y[j], dtype=np.float64).reshape(n) for j in range(m)]))
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        logdet = np.empty((m, H))
+        jitter = np.zeros((m, H))
+        tries = 0
+        while True:
+            rc = self.lib.bopl_fit_model(self.h, n, d, m, H, p(kind_ids), p(X), p(Ym), p(lengthscale), p(variance), p(noise),
+                                         p(jitter), int(bool(want_winv)), int(bool(want_linv)), p(logdet))
+            if rc != _lib.ERR_NUMERIC or tries >= max_tries:
+                break
+            # jitchol: jitter = mean(diag) * 1e-6, then x10 per retry (applied to every instance: the failed one is named
+            # in the message only)
+            base = (variance + noise + 1e-8) * 1e-6
+            jitter = base * (10.0 ** tries)
+            tries += 1
+        self._check(rc)
+        state = GPState(kinds, X, lengthscale, variance, noise, np.repeat(Ym.mean(axis=1)[:, None], H, axis=1), None, None)
+        state.on_device = True
+        state.has_winv, state.has_linv = bool(want_winv), bool(want_linv)
+        state.logdet, state.jitter = logdet, jitter
+        self.state = state
+        self.n, self.d, self.m, self.H = n, d, m, H
+        return state
+
+    def get_factor(self, j, hsel, want_winv=False, want_linv=False):
+        """(L, alpha, Winv, Linv) of attribute j under hyper-sample hsel, read back from the device (`bopl_get_factor`)."""
+        n = self.n
+        L, alpha = np.empty((n, n)), np.empty(n)
+        Winv = np.empty((n, n)) if want_winv else None
+        Linv = np.empty((n, n)) if want_linv else None
+        p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        self._check(self.lib.bopl_get_factor(self.h, int(j), int(hsel), p(L), p(alpha), p(Winv), p(Linv)))
+        return L, alpha, Winv, Linv
+
+    def log_marginal(self, X, Yc, kinds, variance, lengthscale, noise, want_grad=True):
+        """Log marginal likelihood (+ gradient wrt variance, lengthscales, noise) of G independent GPs on the same inputs:
+        one batched likelihood evaluation of MAP / HMC (`bopl_log_marginal`).  Yc (G,n) centred targets; variance, noise (G,);
+        lengthscale (G,d).  Returns ll (G,), grad (G,d+2) or None, info (G,) (non-zero: not positive definite)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n, d = X.shape
+        Yc = np.ascontiguousarray(Yc, dtype=np.float64).reshape(-1, n)
+        G = Yc.shape[0]
+        variance = np.ascontiguousarray(variance, dtype=np.float64).reshape(G)
+        noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(G)
+        lengthscale = np.ascontiguousarray(lengthscale, dtype=np.float64).reshape(G, d)
+        kind_ids = np.ascontiguousarray([KERNEL_KINDS[str(k)] for k in np.asarray(kinds).reshape(G)], dtype=np.int32)
+        ll = np.empty(G)
+        grad = np.empty((G, d + 2)) if want_grad else None
+        info = np.zeros(G, dtype=np.int32)
+        p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        self._check(self.lib.bopl_log_marginal(self.h, n, d, G, p(kind_ids), p(X), p(Yc), p(lengthscale), p(variance), p(noise),
+                                               p(ll), p(grad), p(info)))
+        return ll, grad, info
 
     # ------------------------------------------------------------------ posterior (device tensors)
     def cross_cov_dev(self, Xc, hsel, j):

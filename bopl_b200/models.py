@@ -3,7 +3,9 @@
 Same constructor, attributes and method names as the reference.  Every `predict / posterior_*` call runs the
 sm_100a kernels through the C-ABI; the per-attribute Python loop of the reference (multi_outputGP.py:91-141,
 225-246) is replaced by one launch over all attributes.  What stays on the host is what the reference keeps in
-LAPACK once per model update — the Cholesky factorisation (`exact_gaussian_inference.py:44-51`), `dpotrs`, `dpotri`.
+LAPACK once per model update — the Cholesky factorisation (`exact_gaussian_inference.py:44-51`), `dpotrs`, `dpotri` —
+runs on the device too by default (`Engine.fit_model` -> `bopl_fit_model`); `state_from_hyperparameters` below is the
+host/LAPACK form of the same fit (used by `fit_on_device=False`, by `from_reference_model`, and as the tests' comparison).
 
 Hyper-parameter inference (MAP + HMC, `GPyOpt/models/gpmodel.py:109-149`) is outside the hot path and stays on the
 host: `updateModel` runs `bopl_b200/fit.py` (same model, priors and sampler settings as the reference) unless the
@@ -146,7 +148,7 @@ class MultiOutputGP(object):
     analytical_gradient_prediction = True
 
     def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
-                 fixed_hyps=False, device=0, gradients=True, fit_options=None):
+                 fixed_hyps=False, device=0, gradients=True, fit_options=None, fit_on_device=True):
         self.output_dim = output_dim
         self.kernel = [None] * output_dim if kernel is None else kernel          # GPy kernel names ('Mat52', 'rbf', ...)
         self.noise_var = [None] * output_dim if noise_var is None else noise_var
@@ -157,6 +159,7 @@ class MultiOutputGP(object):
         self.name = 'multi-output GP'                                              # checked in core/bopl.py:46,440
         self.gradients = gradients
         self.fit_options = dict(fit_options or {})        # n_burnin, subsample_interval, step_size, leapfrog_steps, max_iters
+        self.fit_on_device = fit_on_device                # False: LAPACK on the host + upload (bopl_set_model), as round 1 did
         self.engine = Engine(device)
         self._hyps = None
         self._h = 0
@@ -202,13 +205,21 @@ class MultiOutputGP(object):
         self._h = 0                                                                 # gpmodel.py:107
 
     def updateModel(self, X_all, Y_all):
-        """multi_outputGP.py:57-62.  Refits every (attribute, hyper-sample) posterior on the host with LAPACK and uploads."""
+        """multi_outputGP.py:57-62.  Refits every (attribute, hyper-sample) posterior: on the device (`bopl_fit_model`:
+        covariance, blocked Cholesky, alpha, K^-1, L^-1 in one batched pass; only X, Y and the hyper-parameters are uploaded)
+        or, with `fit_on_device=False`, on the host with LAPACK followed by an upload of the factors."""
         self.X_all, self.Y_all = X_all, Y_all
         if self._hyps is not None:
             kinds, variance, lengthscale, noise = self._hyps
         else:
             kinds, variance, lengthscale, noise = self._infer_hyperparameters(X_all, Y_all)
-        self._load(state_from_hyperparameters(X_all, Y_all, kinds, variance, lengthscale, noise, self.gradients))
+        if self.fit_on_device:
+            self.state = self.engine.fit_model(X_all, Y_all, kinds, variance, lengthscale, noise,
+                                               want_winv=self.gradients, want_linv=True)
+            self.n_samples = self.state.H
+            self._h = 0                                                             # gpmodel.py:107
+        else:
+            self._load(state_from_hyperparameters(X_all, Y_all, kinds, variance, lengthscale, noise, self.gradients))
 
     def _infer_hyperparameters(self, X_all, Y_all):
         """Per attribute: MAP + HMC hyper-samples on the host (GPyOpt/models/gpmodel.py:109-149); `fixed_hyps=True` keeps

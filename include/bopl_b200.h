@@ -31,7 +31,8 @@ enum bopl_status {
   BOPL_ERR_INVALID = -1,    /* bad argument */
   BOPL_ERR_CUDA = -2,       /* CUDA runtime error (message has the cudaGetErrorString text) */
   BOPL_ERR_STATE = -3,      /* call order: model not set, gradients requested without Winv, ... */
-  BOPL_ERR_UNSUPPORTED = -4 /* shape outside what the kernels are built for */
+  BOPL_ERR_UNSUPPORTED = -4, /* shape outside what the kernels are built for */
+  BOPL_ERR_NUMERIC = -5      /* covariance matrix not positive definite (the caller may retry with jitter, linalg.py:53-78) */
 };
 
 /* GPy kernel `.name` -> tag.  GPy/kern/src/stationary.py:516 (Mat52), :427 (Mat32), :581 (ExpQuad), rbf.py:22 (rbf). */
@@ -78,6 +79,38 @@ const char* bopl_build_info(void);
 int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
                    const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
                    const double* L_h, const double* alpha_h, const double* Winv_h, const double* Linv_h);
+
+/* ---- model fit on the device ------------------------------------------------------------------
+ * Same result as bopl_set_model, but the per-(attribute, hyper-sample) posterior state is COMPUTED on the device from the
+ * data and the hyper-parameters: K = K(X,X) + (noise + 1e-8 + jitter) I, blocked Cholesky on the FP64 tensor pipe,
+ * alpha = K^-1 (y - mean(y)), and (optionally) K^-1 and L^-1 — what the reference does on the host per model update in
+ * GPy/core/gp.py:52-62,247-260 (mean-centring normaliser of this fork, util/normalizer.py:57-72),
+ * inference/latent_function_inference/exact_gaussian_inference.py:44-51 (jitchol/dpotrf, dpotrs) and posterior.py:171-191
+ * (dpotri), called from GPyOpt/models/gpmodel.py:96-107 for each of models/multi_outputGP.py:57-62's attributes.
+ * All HOST pointers.  Y_h [m*n] raw targets of the m attributes; jitter_h [m*H] extra diagonal or NULL;
+ * want_winv / want_linv as the Winv_h / Linv_h arguments of bopl_set_model; logdet_h [m*H] (log|K|) may be NULL.
+ * Returns BOPL_ERR_NUMERIC when a matrix is not positive definite (the message names the instance); the handle then has
+ * no model. */
+int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
+                   const double* jitter_h, int want_winv, int want_linv, double* logdet_h);
+
+/* Log marginal likelihood of G independent exact GPs on the same inputs and its gradient with respect to the kernel
+ * hyper-parameters — one likelihood evaluation of MAP / HMC hyper-parameter inference (GPyOpt/models/gpmodel.py:109-149 ->
+ * GPy/core/gp.py:247-266: exact_gaussian_inference.py:44-65 for log p(y) and dL/dK = 0.5 (alpha alpha^T - K^-1);
+ * kern/src/stationary.py:191-215,236-245 for dL/d variance and dL/d lengthscale; likelihoods/gaussian.py:64-71 for
+ * dL/d noise).  Does not touch the handle's model.  All HOST pointers.
+ *   kern_kind_h [G]; X_h [n*d]; Yc_h [G*n] CENTRED targets; ell_h [G*d]; var_h, noise_h [G] (1e-8 is added as the reference does)
+ *   ll_h [G]; grad_h [G*(d+2)] = (d/d variance, d/d ell_0..d-1, d/d noise); info_h [G] = 0 or 1 + index of the failed pivot
+ *   (ll and grad of such an instance are not meaningful). */
+int bopl_log_marginal(bopl_handle* h, int n, int d, int G, const int* kern_kind_h, const double* X_h, const double* Yc_h,
+                      const double* ell_h, const double* var_h, const double* noise_h, double* ll_h, double* grad_h,
+                      int* info_h);
+
+/* Read back the posterior state of attribute j under hyper-sample hsel in the reference's own layout (tests, checkpoints):
+ * L_h [n*n] lower Cholesky factor (row-major, zeros above the diagonal), alpha_h [n], Winv_h [n*n], Linv_h [n*n].
+ * Any pointer may be NULL; Winv / Linv must have been loaded or fitted.  HOST pointers. */
+int bopl_get_factor(bopl_handle* h, int j, int hsel, double* L_h, double* alpha_h, double* Winv_h, double* Linv_h);
 
 /* ---- kernel (1): cross-covariance ------------------------------------------------------------------------
  * K(Xc, X) for attribute j under hyper-sample hsel -> K [N*n].  Replaces Stationary.K / _scaled_dist /
