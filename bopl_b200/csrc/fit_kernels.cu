@@ -36,8 +36,7 @@ constexpr int FSTAGES = 3;
 constexpr int FSTAGE_DBL = 2 * FTILE;
 constexpr size_t GEMM_SMEM = (size_t)FSTAGES * FSTAGE_DBL * sizeof(double);   // 96 KB
 constexpr int DS = FB + 1;                  // row stride of the diagonal block in shared memory
-constexpr int XP = FB * (FB + 1) / 2;       // packed lower triangle
-constexpr size_t DIAG_SMEM = ((size_t)FB * DS + XP + FB) * sizeof(double);
+constexpr size_t DIAG_SMEM = ((size_t)FB * DS + 3 * FB) * sizeof(double);
 
 // One GP instance (attribute j, hyper-sample h) of a batched fit.  All device pointers.
 struct FitDev {
@@ -120,6 +119,67 @@ __device__ __forceinline__ void zero_acc(double (&acc)[2][16][2]) {
     for (int nt = 0; nt < 16; ++nt) acc[mi][nt][0] = acc[mi][nt][1] = 0.0;
 }
 
+// Narrow form for latency-bound chains (L^-T block rows): acc += A[32 x 16 nk] * B[128 x 16 nk]^T.  Warp w owns rows
+// 16 (w & 1).. of A against rows 32 (w >> 1).. of B; thread (g, t): acc[mi][nt][e] = C[16 (w&1) + 8mi + g][32 (w>>1) + 8nt + 2t + e].
+constexpr int F32_STAGES = 4;
+constexpr int F32_STAGE_DBL = 32 * TRSM_BK + FTILE;
+constexpr size_t GEMM32_SMEM = (size_t)F32_STAGES * F32_STAGE_DBL * sizeof(double);   // 80 KB
+__device__ __forceinline__ void gemm_nt32(double (&acc)[2][4][2], const double* __restrict__ A, size_t lda,
+                                          const double* __restrict__ B, size_t ldb, int nk, double* P, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int Rw = (warp & 1) * 16, Cw = (warp >> 1) * 32, swz = (g & 1) << 2;
+#pragma unroll
+  for (int s = 0; s < F32_STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<32, TRSM_BK, FNT>(P + s * F32_STAGE_DBL, A + (size_t)s * TRSM_BK, lda, tid);
+      load_tile<FB, TRSM_BK, FNT>(P + s * F32_STAGE_DBL + 32 * TRSM_BK, B + (size_t)s * TRSM_BK, ldb, tid);
+    }
+    cp_async_commit();
+  }
+  for (int it = 0; it < nk; ++it) {
+    cp_async_wait<F32_STAGES - 2>();
+    __syncthreads();
+    const int nxt = it + F32_STAGES - 1;
+    if (nxt < nk) {
+      double* st = P + (nxt % F32_STAGES) * F32_STAGE_DBL;
+      load_tile<32, TRSM_BK, FNT>(st, A + (size_t)nxt * TRSM_BK, lda, tid);
+      load_tile<FB, TRSM_BK, FNT>(st + 32 * TRSM_BK, B + (size_t)nxt * TRSM_BK, ldb, tid);
+    }
+    cp_async_commit();
+    const double* As = P + (it % F32_STAGES) * F32_STAGE_DBL;
+    const double* Bs = As + 32 * TRSM_BK;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ch = ((t + 4 * kk) ^ swz) << 1;
+      double2 a[2], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) a[mi] = *reinterpret_cast<const double2*>(As + (Rw + 8 * mi + g) * TRSM_BK + ch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const double2*>(Bs + (Cw + 8 * u + g) * TRSM_BK + ch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) dmma(acc[mi][u][0], acc[mi][u][1], a[mi].x, b[u].x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) dmma(acc[mi][u][0], acc[mi][u][1], a[mi].y, b[u].y);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+__device__ __forceinline__ void store_tile32(const double (&acc)[2][4][2], double* C, size_t ldc, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int Rw = (warp & 1) * 16, Cw = (warp >> 1) * 32;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<double2*>(C + (size_t)(Rw + 8 * mi + g) * ldc + Cw + 8 * nt + 2 * t) = make_double2(acc[mi][nt][0], acc[mi][nt][1]);
+}
+
 // C[row][col] (128 x 128 tile, leading dimension ldc, 16-byte aligned rows) = sign * acc (+ C when ACCUM)
 template <bool ACCUM>
 __device__ __forceinline__ void store_tile(const double (&acc)[2][16][2], double* C, size_t ldc, double sign, int tid) {
@@ -189,94 +249,152 @@ __global__ void __launch_bounds__(256) fit_cov_kernel(const FitDev* fits, int d,
 
 // ---------------------------------------------------------------------------------------------- diagonal block
 // Cholesky factor of the 128 x 128 diagonal block b, its inverse (plain + DMMA-fragment order) and sum(log L_ii).
-// One CTA per instance.  Column sweep on the unscaled columns (s_ik = a_ik - sum_j s_ij s_kj / s_jj; L = S D^-1/2) so that
-// a column needs ONE CTA barrier.
-__global__ void __launch_bounds__(FNT, 1) fit_potrf_diag_kernel(const FitDev* fits, int b, int n_pad) {
-  extern __shared__ __align__(128) double sm[];
-  double* S = sm;                // [128][129]
-  double* Xp = S + FB * DS;      // packed lower triangle of the inverse
-  double* sd = Xp + XP;          // [128] sqrt of the pivots
-  const FitDev f = fits[blockIdx.x];
-  const int tid = threadIdx.x;
-  double* Ab = f.A + (size_t)b * FB * n_pad + (size_t)b * FB;
-  for (int idx = tid; idx < FB * FB; idx += FNT) {
-    const int r = idx >> 7, c = idx & 127;
-    S[r * DS + c] = (c <= r) ? Ab[(size_t)r * n_pad + c] : 0.0;
-  }
-  __shared__ int bad;
-  if (tid == 0) bad = 0;
-  const int half = tid & 1, rloc = tid >> 1;
-  for (int j = 0; j < FB; ++j) {
+// One CTA of 16 x 16 threads per instance; thread (ty, tx) keeps the 8 x 8 elements (ty + 16 ia, tx + 16 kb) of the block
+// in REGISTERS (cyclic distribution: every thread stays busy until the last columns).  Both sweeps publish one vector per
+// step through a double-buffered shared-memory line, so a step costs one CTA barrier:
+//   factorisation  column sweep on the unscaled columns, s_ik -= s_ij s_kj / s_jj (L = S D^-1/2 afterwards);
+//   inversion      forward substitution on all columns of the identity at once: row j of X is final after step j-1,
+//                  x_j /= l_jj is published, every later row subtracts l_ij x_j.
+template <int JB>
+__device__ __forceinline__ void chol_sweep16(double (&a)[8][8], double* colbuf, int tx, int ty, int jbase, int& bad) {
+#pragma unroll 1
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * JB + jj;
+    double* buf = colbuf + (j & 1) * FB;
+    if (tx == jj) {
+#pragma unroll
+      for (int ia = JB; ia < 8; ++ia) buf[ty + 16 * ia] = a[ia][JB];
+    }
     __syncthreads();
-    double dj = S[j * DS + j];
+    double dj = buf[j];
     if (!(dj > 0.0)) {
-      if (tid == 0 && bad == 0) bad = b * FB + j + 1;
+      if (bad == 0) bad = jbase + j + 1;
       dj = 1.0;
     }
     const double rinv = 1.0 / dj;
-    const int i = j + 1 + rloc;
-    if (i < FB) {
-      const double lij = S[i * DS + j] * rinv;
-      double* Si = S + i * DS;
-      for (int k = j + 1 + half; k <= i; k += 2) Si[k] = fma(-lij, S[k * DS + j], Si[k]);
+    double ri[8];
+#pragma unroll
+    for (int ia = JB; ia < 8; ++ia) ri[ia] = buf[ty + 16 * ia] * rinv;
+#pragma unroll
+    for (int kb = JB; kb < 8; ++kb) {
+      const double ck = buf[tx + 16 * kb];
+      if (kb > JB || tx > jj) {
+#pragma unroll
+        for (int ia = kb; ia < 8; ++ia) a[ia][kb] = fma(-ri[ia], ck, a[ia][kb]);
+      }
+    }
+  }
+}
+
+template <int JB>
+__device__ __forceinline__ void inv_sweep16(double (&x)[8][8], const double* S, double* rowbuf, int tx, int ty) {
+#pragma unroll 1
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * JB + jj;
+    double* buf = rowbuf + (j & 1) * FB;
+    if (ty == jj) {
+      const double ljj = S[j * DS + j];
+#pragma unroll
+      for (int cb = 0; cb <= JB; ++cb) {
+        x[JB][cb] = x[JB][cb] / ljj;
+        buf[tx + 16 * cb] = x[JB][cb];
+      }
+    }
+    __syncthreads();
+    double xr[8];
+#pragma unroll
+    for (int cb = 0; cb <= JB; ++cb) xr[cb] = buf[tx + 16 * cb];
+#pragma unroll
+    for (int ia = JB; ia < 8; ++ia) {
+      if (ia > JB || ty > jj) {
+        const double lij = S[(ty + 16 * ia) * DS + j];
+#pragma unroll
+        for (int cb = 0; cb <= JB; ++cb) x[ia][cb] = fma(-lij, xr[cb], x[ia][cb]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FNT, 1) fit_potrf_diag_kernel(const FitDev* fits, int b, int n_pad) {
+  extern __shared__ __align__(128) double sm[];
+  double* S = sm;                // [128][129] L, then L^-1
+  double* line = S + FB * DS;    // [2][128] published column / row
+  double* sd = line + 2 * FB;    // [128] sqrt of the pivots
+  const FitDev f = fits[blockIdx.x];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double* Ab = f.A + (size_t)b * FB * n_pad + (size_t)b * FB;
+  double a[8][8];
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) a[ia][kb] = (kb <= ia) ? Ab[(size_t)(ty + 16 * ia) * n_pad + tx + 16 * kb] : 0.0;
+  int bad = 0;
+  chol_sweep16<0>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<1>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<2>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<3>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<4>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<5>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<6>(a, line, tx, ty, b * FB, bad);
+  chol_sweep16<7>(a, line, tx, ty, b * FB, bad);
+  if (tx == ty) {
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia) {
+      double dj = a[ia][ia];
+      if (!(dj > 0.0)) dj = 1.0;
+      sd[ty + 16 * ia] = sqrt(dj);
     }
   }
   __syncthreads();
-  if (tid < FB) {
-    double dj = S[tid * DS + tid];
-    if (!(dj > 0.0)) dj = 1.0;
-    sd[tid] = sqrt(dj);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < FB * FB; idx += FNT) {
-    const int r = idx >> 7, c = idx & 127;
-    if (c < r) S[r * DS + c] = S[r * DS + c] / sd[c];
-    else if (c == r) S[r * DS + c] = sd[c];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < FB * FB; idx += FNT) {
-    const int r = idx >> 7, c = idx & 127;
-    Ab[(size_t)r * n_pad + c] = (c <= r) ? S[r * DS + c] : 0.0;
-  }
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int i = ty + 16 * ia, k = tx + 16 * kb;
+      double v = 0.0;
+      if (kb <= ia) v = (k < i) ? a[ia][kb] / sd[k] : (k == i ? sd[k] : 0.0);
+      S[i * DS + k] = v;
+      if (kb <= ia) Ab[(size_t)i * n_pad + k] = v;
+    }
   if (tid < 32) {
     double s = 0.0;
     for (int k = tid; k < FB; k += 32) s += log(sd[k]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (tid == 0) {
-      f.logdiag[b] = s;
-      if (bad && *f.info == 0) *f.info = bad;
-    }
+    if (tid == 0) f.logdiag[b] = s;
   }
-  // inverse: column c by forward substitution, two threads per column (k split by parity), rows in lock-step per warp
-  {
-    const int c = tid >> 1;
-    const int cmin = (tid & ~31) >> 1;
-    if (half == 0) Xp[c * (c + 1) / 2 + c] = 1.0 / S[c * DS + c];
-    __syncwarp();
-    for (int r = cmin + 1; r < FB; ++r) {
-      double s = 0.0;
-      if (c < r) {
-        const double* Sr = S + r * DS;
-        for (int k = c + half; k < r; k += 2) s = fma(Sr[k], Xp[k * (k + 1) / 2 + c], s);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (c < r && half == 0) Xp[r * (r + 1) / 2 + c] = -s / S[r * DS + r];
-      __syncwarp();
+  if (bad && tid == 0 && *f.info == 0) *f.info = bad;   // every thread saw the same pivots
+  __syncthreads();
+  // inverse
+  double x[8][8];
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) x[ia][cb] = (ia == cb && tx == ty) ? 1.0 : 0.0;
+  inv_sweep16<0>(x, S, line, tx, ty);
+  inv_sweep16<1>(x, S, line, tx, ty);
+  inv_sweep16<2>(x, S, line, tx, ty);
+  inv_sweep16<3>(x, S, line, tx, ty);
+  inv_sweep16<4>(x, S, line, tx, ty);
+  inv_sweep16<5>(x, S, line, tx, ty);
+  inv_sweep16<6>(x, S, line, tx, ty);
+  inv_sweep16<7>(x, S, line, tx, ty);
+  __syncthreads();               // every read of L is done: S becomes L^-1
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) {
+      const int i = ty + 16 * ia, c = tx + 16 * cb;
+      S[i * DS + c] = (c <= i) ? x[ia][cb] : 0.0;
     }
-  }
   __syncthreads();
   double* Db = f.Dinv + (size_t)b * FB * FB;
-  for (int idx = tid; idx < FB * FB; idx += FNT) {
-    const int r = idx >> 7, c = idx & 127;
-    Db[idx] = (c <= r) ? Xp[r * (r + 1) / 2 + c] : 0.0;
-  }
+  for (int idx = tid; idx < FB * FB; idx += FNT) Db[idx] = S[(idx >> 7) * DS + (idx & 127)];
   double* Fb = f.DinvFrag + (size_t)b * 136 * 64;
   for (int idx = tid; idx < 136 * 64; idx += FNT) {
     const int fi = idx >> 6, w = idx & 63, lane = w >> 1, e = w & 1;
     const int g = lane >> 2, t = lane & 3;
-    const int r = 8 * c_frag_nt[fi] + g, c = 8 * c_frag_kt[fi] + 2 * t + e;
-    Fb[idx] = (c <= r) ? Xp[r * (r + 1) / 2 + c] : 0.0;
+    Fb[idx] = S[(8 * c_frag_nt[fi] + g) * DS + 8 * c_frag_kt[fi] + 2 * t + e];
   }
 }
 
@@ -309,68 +427,107 @@ __global__ void __launch_bounds__(FNT, 1) fit_syrk_kernel(const FitDev* fits, in
 }
 
 // ---------------------------------------------------------------------------------------------- alpha
-// alpha = L^-T L^-1 y by blocked substitution with the inverted diagonal blocks; one CTA of 512 threads per instance.
-// Also packs the staged blocks of the posterior kernel and y^T alpha.
-constexpr int SNT = 512;
+// alpha = L^-T L^-1 y by blocked (left-looking) substitution with the inverted diagonal blocks; one CTA of 1024 threads per
+// instance, every warp keeps four independent row streams in flight.  Also packs the staged blocks of the posterior kernel
+// and y^T alpha.
+constexpr int SNT = 1024;
+constexpr int SNW = SNT / 32;
+
+// out[r] (r = warp + 32 i, i < 4) = sum_{c < ncols} M[r][c] * v[c] for the 128 rows of a block; ncols a multiple of 128.
+__device__ __forceinline__ void rows_dot4(const double* __restrict__ M, size_t ld, int ncols, const double* v, double (&out)[4],
+                                          int warp, int lane) {
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c0 = 0; c0 < ncols; c0 += 128) {
+    const double4 vv = *reinterpret_cast<const double4*>(v + c0 + 4 * lane);
+    double4 m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const double4*>(M + (size_t)(warp + 32 * i) * ld + c0 + 4 * lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[i] = fma(m[i].x, vv.x, s[i]);
+      s[i] = fma(m[i].y, vv.y, s[i]);
+      s[i] = fma(m[i].z, vv.z, s[i]);
+      s[i] = fma(m[i].w, vv.w, s[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = s[i];
+}
+
+// part[warp][c] = sum over this warp's rows r (r = warp + 32 i < nrows) of M[r][c] * v[r], c = 4 lane .. 4 lane + 3 (128 columns).
+__device__ __forceinline__ void cols_dot(const double* __restrict__ M, size_t ld, int nrows, const double* v, double* part, int warp,
+                                         int lane) {
+  double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
+  int r = warp;
+  for (; r + 96 < nrows; r += 128) {
+    double4 m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const double4*>(M + (size_t)(r + 32 * i) * ld + 4 * lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double vr = v[r + 32 * i];
+      s.x = fma(m[i].x, vr, s.x);
+      s.y = fma(m[i].y, vr, s.y);
+      s.z = fma(m[i].z, vr, s.z);
+      s.w = fma(m[i].w, vr, s.w);
+    }
+  }
+  for (; r < nrows; r += 32) {
+    const double4 m = *reinterpret_cast<const double4*>(M + (size_t)r * ld + 4 * lane);
+    const double vr = v[r];
+    s.x = fma(m.x, vr, s.x);
+    s.y = fma(m.y, vr, s.y);
+    s.z = fma(m.z, vr, s.z);
+    s.w = fma(m.w, vr, s.w);
+  }
+  *reinterpret_cast<double4*>(part + warp * FB + 4 * lane) = s;
+}
+
 __global__ void __launch_bounds__(SNT, 1) fit_solve_kernel(const FitDev* fits, int n, int d, int n_pad, int pad) {
   extern __shared__ __align__(128) double sm[];
-  double* rhs = sm;              // [n_pad]
-  double* zb = rhs + n_pad;      // [128]
+  double* rhs = sm;                 // [n_pad]  y, then z = L^-1 y, then alpha
+  double* tmp = rhs + n_pad;        // [128]
+  double* part = tmp + FB;          // [32][128]
   const FitDev f = fits[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nblk = n_pad / FB;
-  constexpr int NW = SNT / 32;
   for (int i = tid; i < n_pad; i += SNT) rhs[i] = (i >= pad) ? f.y[i - pad] : 0.0;
   __syncthreads();
-  // forward: z_b = Dinv_b rhs_b; rhs_i += (-L)(i,b) z_b for the rows below
+  // forward: z_b = Dinv_b (y_b + sum_{k<b} (-L)(b,k) z_k)
   for (int b = 0; b < nblk; ++b) {
-    const double* Db = f.Dinv + (size_t)b * FB * FB;
-    for (int r = warp; r < FB; r += NW) {
-      const double4 dv = *reinterpret_cast<const double4*>(Db + (size_t)r * FB + 4 * lane);
-      const double* rb = rhs + b * FB + 4 * lane;
-      double s = dv.x * rb[0];
-      s = fma(dv.y, rb[1], s);
-      s = fma(dv.z, rb[2], s);
-      s = fma(dv.w, rb[3], s);
+    double o[4];
+    rows_dot4(f.A + (size_t)b * FB * n_pad, n_pad, b * FB, rhs, o, warp, lane);
+    if (lane == 0) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) zb[r] = s;
+      for (int i = 0; i < 4; ++i) tmp[warp + 32 * i] = rhs[b * FB + warp + 32 * i] + o[i];
     }
     __syncthreads();
-    const double z0 = zb[4 * lane], z1 = zb[4 * lane + 1], z2 = zb[4 * lane + 2], z3 = zb[4 * lane + 3];
-    if (tid < FB) rhs[b * FB + tid] = zb[tid];
-    for (int i = (b + 1) * FB + warp; i < n_pad; i += NW) {
-      const double4 lv = *reinterpret_cast<const double4*>(f.A + (size_t)i * n_pad + b * FB + 4 * lane);
-      double s = lv.x * z0;
-      s = fma(lv.y, z1, s);
-      s = fma(lv.z, z2, s);
-      s = fma(lv.w, z3, s);
+    rows_dot4(f.Dinv + (size_t)b * FB * FB, FB, FB, tmp, o, warp, lane);
+    if (lane == 0) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) rhs[i] += s;
+      for (int i = 0; i < 4; ++i) rhs[b * FB + warp + 32 * i] = o[i];
     }
     __syncthreads();
   }
-  // backward: alpha_b = Dinv_b^T rhs_b; rhs_c += sum_{r in block b} (-L)[r][c] alpha_b[r] for the columns left of the block
+  // backward: alpha_b = Dinv_b^T (z_b + sum_{k>b} (-L)(k,b)^T alpha_k)
   for (int b = nblk - 1; b >= 0; --b) {
-    const double* Db = f.Dinv + (size_t)b * FB * FB;
+    cols_dot(f.A + (size_t)(b + 1) * FB * n_pad + (size_t)b * FB, n_pad, (nblk - 1 - b) * FB, rhs + (b + 1) * FB, part, warp, lane);
+    __syncthreads();
     if (tid < FB) {
-      double s = 0.0;
-      for (int r = tid; r < FB; ++r) s = fma(Db[(size_t)r * FB + tid], rhs[b * FB + r], s);
-      zb[tid] = s;
+      double s = rhs[b * FB + tid];
+      for (int w = 0; w < SNW; ++w) s += part[w * FB + tid];
+      tmp[tid] = s;
     }
     __syncthreads();
-    if (tid < FB) rhs[b * FB + tid] = zb[tid];
-    for (int c = tid; c < b * FB; c += SNT) {
-      const double* col = f.A + (size_t)b * FB * n_pad + c;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-      for (int r = 0; r < FB; r += 4) {
-        s0 = fma(col[(size_t)r * n_pad], zb[r], s0);
-        s1 = fma(col[(size_t)(r + 1) * n_pad], zb[r + 1], s1);
-        s2 = fma(col[(size_t)(r + 2) * n_pad], zb[r + 2], s2);
-        s3 = fma(col[(size_t)(r + 3) * n_pad], zb[r + 3], s3);
-      }
-      rhs[c] += (s0 + s1) + (s2 + s3);
+    cols_dot(f.Dinv + (size_t)b * FB * FB, FB, FB, tmp, part, warp, lane);
+    __syncthreads();
+    if (tid < FB) {
+      double s = 0.0;
+      for (int w = 0; w < SNW; ++w) s += part[w * FB + tid];
+      rhs[b * FB + tid] = s;
     }
     __syncthreads();
   }
@@ -383,53 +540,59 @@ __global__ void __launch_bounds__(SNT, 1) fit_solve_kernel(const FitDev* fits, i
     }
   }
   // y^T alpha, fixed order
-  __shared__ double part[SNT / 32];
   double s = 0.0;
   for (int i = pad + tid; i < n_pad; i += SNT) s = fma(f.y[i - pad], rhs[i], s);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) part[warp] = s;
+  __syncthreads();
+  if (lane == 0) tmp[warp] = s;
   __syncthreads();
   if (tid == 0) {
     double tot = 0.0;
-    for (int w = 0; w < NW; ++w) tot += part[w];
+    for (int w = 0; w < SNW; ++w) tot += tmp[w];
     *f.quad = tot;
   }
 }
 
 // ---------------------------------------------------------------------------------------------- inverse factor and K^-1
-// U = L^-T, block row b: U(b,b) = Dinv_b^T; U(b,i) = [sum_{k=b}^{i-1} U(b,k) (-L)(i,k)^T] Dinv_i^T for i > b.  grid (nblk, G).
+// U = L^-T in strips of 32 rows (the rows of U are independent of one another): strip s of block row b holds
+// U(b,b) = Dinv_b^T on the diagonal, then U(b,i) = [sum_{k=b}^{i-1} U(b,k) (-L)(i,k)^T] Dinv_i^T for i > b, left to right.
+// grid (4 nblk, G): the chain of a strip is serial in i, so narrow strips shorten the critical path 4x and fill the SMs.
 __global__ void __launch_bounds__(FNT, 1) fit_linvT_kernel(const FitDev* fits, int n_pad) {
   extern __shared__ __align__(128) double sm[];
   const FitDev f = fits[blockIdx.y];
-  const int b = blockIdx.x, tid = threadIdx.x, nblk = n_pad / FB;
-  double* Ub = f.U + (size_t)b * FB * n_pad;
+  const int b = blockIdx.x >> 2, strip = blockIdx.x & 3, tid = threadIdx.x, nblk = n_pad / FB;
+  double* Ub = f.U + ((size_t)b * FB + 32 * strip) * n_pad;     // first row of the strip
   {
     const double* Db = f.Dinv + (size_t)b * FB * FB;
-    // transposed copy through shared memory (32 x 32 sub-tiles)
+    // U[R0 + r][b FB + c] = Dinv_b[c][32 strip + r]: transposed copy through shared memory, 32 x 32 at a time
     double* tile = sm;   // [32][33]
-    for (int sub = 0; sub < 16; ++sub) {
-      const int sr = (sub >> 2) * 32, sc = (sub & 3) * 32;
+    for (int sub = 0; sub < 4; ++sub) {
       __syncthreads();
-      for (int idx = tid; idx < 1024; idx += FNT) tile[(idx >> 5) * 33 + (idx & 31)] = Db[(size_t)(sr + (idx >> 5)) * FB + sc + (idx & 31)];
+      for (int idx = tid; idx < 1024; idx += FNT) tile[(idx >> 5) * 33 + (idx & 31)] = Db[(size_t)(32 * sub + (idx >> 5)) * FB + 32 * strip + (idx & 31)];
       __syncthreads();
-      for (int idx = tid; idx < 1024; idx += FNT)
-        Ub[(size_t)(sc + (idx >> 5)) * n_pad + b * FB + sr + (idx & 31)] = tile[(idx & 31) * 33 + (idx >> 5)];
+      for (int idx = tid; idx < 1024; idx += FNT) Ub[(size_t)(idx >> 5) * n_pad + b * FB + 32 * sub + (idx & 31)] = tile[(idx & 31) * 33 + (idx >> 5)];
     }
   }
   __threadfence_block();
   __syncthreads();
   for (int i = b + 1; i < nblk; ++i) {
-    double acc[2][16][2];
-    zero_acc(acc);
-    gemm_nt(acc, Ub + (size_t)b * FB, n_pad, f.A + (size_t)i * FB * n_pad + (size_t)b * FB, n_pad, (i - b) * (FB / TRSM_BK), sm, tid);
+    double acc[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mi][nt][0] = acc[mi][nt][1] = 0.0;
+    gemm_nt32(acc, Ub + (size_t)b * FB, n_pad, f.A + (size_t)i * FB * n_pad + (size_t)b * FB, n_pad, (i - b) * (FB / TRSM_BK), sm, tid);
     double* T = Ub + (size_t)i * FB;
-    store_tile<false>(acc, T, n_pad, 1.0, tid);
+    store_tile32(acc, T, n_pad, tid);
     __threadfence_block();
     __syncthreads();
-    zero_acc(acc);
-    gemm_nt(acc, T, n_pad, f.Dinv + (size_t)i * FB * FB, FB, FB / TRSM_BK, sm, tid);
-    store_tile<false>(acc, T, n_pad, 1.0, tid);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mi][nt][0] = acc[mi][nt][1] = 0.0;
+    gemm_nt32(acc, T, n_pad, f.Dinv + (size_t)i * FB * FB, FB, FB / TRSM_BK, sm, tid);
+    store_tile32(acc, T, n_pad, tid);
     __threadfence_block();
     __syncthreads();
   }
@@ -507,7 +670,7 @@ __global__ void __launch_bounds__(256) lml_grad_kernel(const FitDev* fits, int n
       const int i = i0 + r;
       const double w = 0.5 * (ai[r] * ak - f.Winv[(size_t)i * n + k]);
       if (i == k) {
-        gv += w;
+        gv = fma(w, f.variance, gv);      // K_ii = variance (stationary.py:168-171); the reduction divides by it
         gn += w;
       } else {
         double r2 = 0.0, dq2[MAX_D];
@@ -585,7 +748,7 @@ int ensure_tables(bopl_handle* h) {
   BOPL_CUDA(h, cudaFuncSetAttribute(fit_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   BOPL_CUDA(h, cudaFuncSetAttribute(fit_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
   BOPL_CUDA(h, cudaFuncSetAttribute(fit_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-  BOPL_CUDA(h, cudaFuncSetAttribute(fit_linvT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  BOPL_CUDA(h, cudaFuncSetAttribute(fit_linvT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM32_SMEM));
   BOPL_CUDA(h, cudaFuncSetAttribute(fit_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
   BOPL_CUDA(h, cudaFuncSetAttribute(fit_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (h->device < 64) g_tables_ready[h->device] = true;
@@ -601,7 +764,7 @@ int fit_factorize(bopl_handle* h, const void* fits_dev, int G, const double* X_d
   int rc = ensure_tables(h);
   if (rc) return rc;
   const int n_pad = ((n + FB - 1) / FB) * FB, pad = n_pad - n, nblk = n_pad / FB;
-  if ((size_t)(n_pad + FB) * sizeof(double) > 200 * 1024) return fail(h, BOPL_ERR_UNSUPPORTED, "device fit: n > 25000 training points");
+  if ((size_t)(n_pad + FB + SNW * FB) * sizeof(double) > 200 * 1024) return fail(h, BOPL_ERR_UNSUPPORTED, "device fit: n > 21000 training points");
   fit_prep_kernel<<<dim3(64, G), 256, 0, st>>>(fits, X_dev, n, d, n_pad, pad);
   BOPL_LAUNCH_CHECK(h, "fit_prep_kernel");
   fit_cov_kernel<<<dim3(nblk * (nblk + 1) / 2, G), 256, 0, st>>>(fits, d, n_pad, pad);
@@ -617,10 +780,10 @@ int fit_factorize(bopl_handle* h, const void* fits_dev, int G, const double* X_d
       BOPL_LAUNCH_CHECK(h, "fit_syrk_kernel");
     }
   }
-  fit_solve_kernel<<<G, SNT, (size_t)(n_pad + FB) * sizeof(double), st>>>(fits, n, d, n_pad, pad);
+  fit_solve_kernel<<<G, SNT, (size_t)(n_pad + FB + SNW * FB) * sizeof(double), st>>>(fits, n, d, n_pad, pad);
   BOPL_LAUNCH_CHECK(h, "fit_solve_kernel");
   if (want_inverse) {
-    fit_linvT_kernel<<<dim3(nblk, G), FNT, GEMM_SMEM, st>>>(fits, n_pad);
+    fit_linvT_kernel<<<dim3(4 * nblk, G), FNT, GEMM32_SMEM, st>>>(fits, n_pad);
     BOPL_LAUNCH_CHECK(h, "fit_linvT_kernel");
     if (want_winv) {
       fit_winv_kernel<<<dim3(nblk * (nblk + 1) / 2, G), FNT, GEMM_SMEM, st>>>(fits, n, n_pad, pad);

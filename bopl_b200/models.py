@@ -7,10 +7,10 @@ LAPACK once per model update — the Cholesky factorisation (`exact_gaussian_inf
 runs on the device too by default (`Engine.fit_model` -> `bopl_fit_model`); `state_from_hyperparameters` below is the
 host/LAPACK form of the same fit (used by `fit_on_device=False`, by `from_reference_model`, and as the tests' comparison).
 
-Hyper-parameter inference (MAP + HMC, `GPyOpt/models/gpmodel.py:109-149`) is outside the hot path and stays on the
-host: `updateModel` runs `bopl_b200/fit.py` (same model, priors and sampler settings as the reference) unless the
-hyper-samples were supplied with `set_hyperparameter_samples(...)`; a live reference model can be wrapped with
-`from_reference_model`.
+Hyper-parameter inference (MAP + HMC, `GPyOpt/models/gpmodel.py:109-149`): `updateModel` runs `bopl_b200/fit.py` (same
+model, priors and sampler settings as the reference; the optimiser / sampler logic on the host, every likelihood + gradient
+evaluation of all attributes as one batched device call) unless the hyper-samples were supplied with
+`set_hyperparameter_samples(...)`; a live reference model can be wrapped with `from_reference_model`.
 """
 import numpy as np
 from scipy.linalg import lapack
@@ -224,11 +224,17 @@ class MultiOutputGP(object):
     def _infer_hyperparameters(self, X_all, Y_all):
         """Per attribute: MAP + HMC hyper-samples on the host (GPyOpt/models/gpmodel.py:109-149); `fixed_hyps=True` keeps
         the MAP estimate only."""
-        from .fit import fit_hyperparameter_samples
+        from .fit import fit_hyperparameter_samples, fit_hyperparameter_samples_device
         X = np.asarray(X_all, dtype=np.float64)
         m, d = self.output_dim, X.shape[1]
         H = 1 if self.fixed_hyps else self.n_samples
         kinds = np.array([k if k is not None else "Mat52" for k in self.kernel])
+        if self.fit_on_device:
+            variance, lengthscale, noise = fit_hyperparameter_samples_device(
+                self.engine, X, [Y_all[j] for j in range(m)], kinds, self.ARD, self.exact_feval, self.noise_var, n_samples=H,
+                hmc=not self.fixed_hyps, **self.fit_options)
+            self.n_samples = H
+            return kinds, variance, lengthscale, noise
         variance, lengthscale, noise = np.empty((m, H)), np.empty((m, H, d)), np.empty((m, H))
         for j in range(m):
             v, l, s = fit_hyperparameter_samples(X, Y_all[j], str(kinds[j]), bool(self.ARD[j]), bool(self.exact_feval[j]),

@@ -86,8 +86,9 @@ def apply_optimizer(optimizer, x0, f, df=None, f_df=None, duplicate_manager=None
 class LockstepBatcher(object):
     """Gathers one `f_df(x)` request from every still-running worker into a single `f_df_batch(X)` call."""
 
-    def __init__(self, f_df_batch, n_workers):
+    def __init__(self, f_df_batch, n_workers, with_ids=False):
         self.f_df_batch = f_df_batch
+        self.with_ids = with_ids            # True: f_df_batch(X, ids) also gets the worker ids of the rows
         self.active = n_workers
         self.cv = threading.Condition()
         self.pending = {}
@@ -99,7 +100,7 @@ class LockstepBatcher(object):
         ids = sorted(self.pending)
         X = np.stack([self.pending[i] for i in ids])
         try:
-            fx, g = self.f_df_batch(X)
+            fx, g = self.f_df_batch(X, ids) if self.with_ids else self.f_df_batch(X)
             fx = np.asarray(fx, dtype=np.float64).reshape(len(ids))
             g = np.asarray(g, dtype=np.float64).reshape(len(ids), -1)
             for k, i in enumerate(ids):

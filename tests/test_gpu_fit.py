@@ -186,3 +186,38 @@ def test_log_marginal_and_gradient_match_host_objective(kind, ard_shared):
             a_d = eng.log_marginal(p["X"], Yc, [kind] * m, var, dn, noise, want_grad=False)[0]
             fd = (a_u - a_d) / (2 * h * arr[:, col])
             assert np.all(np.abs(fd - grad[:, 1 + col]) <= 1e-4 * np.abs(grad[:, 1 + col]) + 1e-5)
+
+
+def test_device_hyperparameter_inference_matches_host_inference():
+    """MAP + HMC with every likelihood evaluation on the device (lock-step over the attributes) against the host/LAPACK run
+    with the same per-attribute random streams: the MAP estimates agree to optimiser tolerance, the short HMC chains land
+    on the same hyper-samples (the two likelihoods differ by rounding only)."""
+    from bopl_b200.fit import GPObjective, fit_hyperparameter_samples, fit_hyperparameter_samples_device, map_estimate
+    from bopl_b200.models import MultiOutputGP
+    p = make_problem("dtlz2a_quad", n=60, N=4)
+    m = p["m"]
+    eng = MultiOutputGP(m).engine
+    Ys = [p["Y"][j] for j in range(m)]
+    kinds, ARD, ef, nv = ["Mat52"] * m, [True, True, False, True], [True, True, True, False], [None] * m
+    kw = dict(n_samples=3, n_burnin=4, subsample_interval=2, leapfrog_steps=5)
+    v, l, s = fit_hyperparameter_samples_device(eng, p["X"], Ys, kinds, ARD, ef, nv,
+                                                rngs=[np.random.RandomState(7 + j) for j in range(m)], **kw)
+    for j in range(m):
+        v1, l1, s1 = fit_hyperparameter_samples(p["X"], Ys[j], kinds[j], ARD[j], ef[j], nv[j], rng=np.random.RandomState(7 + j), **kw)
+        assert np.allclose(v[j], v1, rtol=1e-4), (j, v[j], v1)
+        assert np.allclose(l[j], l1, rtol=1e-4), (j, l[j], l1)
+        assert np.allclose(s[j], s1, rtol=1e-4), (j, s[j], s1)
+
+
+def test_update_model_infers_hyperparameters_and_fits_on_device():
+    """MultiOutputGP.updateModel(X, Y) with no hyper-parameters supplied: MAP (fixed_hyps) on the device, then the device fit;
+    the posterior interpolates the (noise-free) training targets."""
+    from bopl_b200.models import MultiOutputGP
+    p = make_problem("dtlz1a_linear", n=40, N=4)
+    gm = MultiOutputGP(p["m"], exact_feval=[True] * p["m"], fixed_hyps=True, fit_options=dict(max_iters=60))
+    gm.updateModel(p["X"], [p["Y"][j][:, None] for j in range(p["m"])])
+    assert gm.state.on_device and gm.number_of_hyps_samples() == 1
+    F = gm.posterior_mean_at_evaluated_points()
+    assert np.max(np.abs(F - p["Y"])) <= 1e-3 * np.max(np.abs(p["Y"]))
+    mu, var = gm.predict(p["Xc"])
+    assert mu.shape == (p["m"], 4) and np.all(var > 0)

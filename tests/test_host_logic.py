@@ -256,3 +256,39 @@ def test_hyperparameter_objective_gradient_and_map_fit():
     v, l, s = fit_hyperparameter_samples(X, Y, n_samples=4, n_burnin=10, subsample_interval=2, leapfrog_steps=5, rng=rs)
     assert v.shape == (4,) and l.shape == (4, 3) and s.shape == (4,)
     assert np.all(np.isfinite(l)) and np.all(l > 0) and np.all(v > 0) and len(np.unique(np.round(v, 12))) > 1
+
+
+def test_lockstep_hyperparameter_inference_equals_per_attribute_runs():
+    """fit.py's lock-step drivers (one batched likelihood call per step for all attributes) reproduce the sequential
+    per-attribute MAP + HMC runs when every attribute draws from its own RandomState.  The batched likelihood is stood in
+    for by the host NumPy/LAPACK one (the device one is compared with it in tests/test_gpu_fit.py)."""
+    from bopl_b200.fit import GPObjective, fit_hyperparameter_samples, fit_hyperparameter_samples_device
+
+    class HostStandIn(object):
+        calls = 0
+
+        def log_marginal(self, X, Yc, kinds, var, ell, noise, want_grad=True):
+            G, d = len(var), X.shape[1]
+            ll, grad, info = np.zeros(G), np.zeros((G, d + 2)), np.zeros(G, dtype=np.int32)
+            for g in range(G):
+                l, gr = GPObjective(X, Yc[g], kinds[g], True, None).host_likelihood(var[g], ell[g], noise[g])
+                if l is None:
+                    info[g] = 1
+                else:
+                    ll[g], grad[g] = l, gr
+            HostStandIn.calls += 1
+            return ll, grad, info
+
+    rs = np.random.RandomState(0)
+    X = rs.uniform(size=(40, 3))
+    Ys = [np.sin(6 * X[:, 0]) + 0.01 * rs.normal(size=40), np.cos(3 * X[:, 1]) + 0.2 * X[:, 2], X[:, 0] * X[:, 1]]
+    kinds, ARD, ef, nv = ["Mat52", "rbf", "Mat32"], [True, True, False], [False, True, False], [None, None, 1e-3]
+    kw = dict(n_samples=3, n_burnin=6, subsample_interval=2, leapfrog_steps=4)
+    v, l, s = fit_hyperparameter_samples_device(HostStandIn(), X, Ys, kinds, ARD, ef, nv,
+                                                rngs=[np.random.RandomState(10 + j) for j in range(3)], **kw)
+    assert v.shape == (3, 3) and l.shape == (3, 3, 3) and s.shape == (3, 3)
+    for j in range(3):
+        v1, l1, s1 = fit_hyperparameter_samples(X, Ys[j], kinds[j], ARD[j], ef[j], nv[j], rng=np.random.RandomState(10 + j), **kw)
+        assert np.allclose(v[j], v1, rtol=1e-7) and np.allclose(l[j], l1, rtol=1e-7) and np.allclose(s[j], s1, rtol=1e-7)
+    # one batched call per leap-frog step, not one per attribute: (6 + 3*2) HMC iterations x 4 steps + 1, plus the MAP steps
+    assert HostStandIn.calls < 12 * 4 + 1 + 200
