@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
-SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu"]
+SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0"]
@@ -26,7 +26,7 @@ SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", 
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
            "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
            "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count", "bopl_fit_model", "bopl_log_marginal",
-           "bopl_get_factor"]
+           "bopl_get_factor", "bopl_path_begin", "bopl_path_eval_host", "bopl_path_length", "bopl_path_end"]
 
 
 class BoplError(RuntimeError):
@@ -118,6 +118,10 @@ def load():
     lib.bopl_uei_host.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, c_int, c_ll,
                                   dp, llp]
     lib.bopl_uei_grad_host.argtypes = [vp, dp, c_int, dp, c_int, c_int, dp, c_int, c_int, dp, dp, c_int, dp, dp]
+    lib.bopl_path_begin.argtypes = [vp, c_int, c_int, dp]
+    lib.bopl_path_eval_host.argtypes = [vp, dp, dp, dp, dp, dp]
+    lib.bopl_path_length.argtypes = [vp]
+    lib.bopl_path_end.argtypes = [vp]
     lib.bopl_launch_count.argtypes = [vp]
     lib.bopl_launch_count.restype = c_ll
     for name in SYMBOLS:

@@ -32,6 +32,7 @@ int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes) {
 }
 
 void free_model(bopl_handle* h) {
+  path_free(h);
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear();
   h->gp_host.clear();

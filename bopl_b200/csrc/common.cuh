@@ -78,6 +78,7 @@ struct bopl_handle {
   double* gh_dev = nullptr; size_t gh_cap = 0;       // staging of the host-buffer value+gradient call
   void* fit_ws = nullptr; size_t fit_ws_bytes = 0;   // workspace of bopl_log_marginal (factor, inverse, K^-1 of every instance)
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
+  void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
   size_t hsmall_cap = 0;
 };
 
@@ -115,6 +116,7 @@ int fail(bopl_handle* h, int code, const std::string& msg);
 
 int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes);
 void free_model(bopl_handle* h);
+void path_free(bopl_handle* h);         // drops the sample path (it refers to the model's factor)
 
 // device-side model fit (fit_kernels.cu); FitDev is private to that translation unit
 size_t fit_dev_struct_bytes();

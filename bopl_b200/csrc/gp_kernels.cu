@@ -524,6 +524,20 @@ int launch_posterior_small(bopl_handle* h, const double* Xc, int N, int hsel, do
   return BOPL_OK;
 }
 
+// V0 = Linv K*(x) of ONE point for every attribute (the sample-path step of path_kernels.cu); K0, V0 -> [m][n] scratch rows.
+int launch_small_solve1(bopl_handle* h, const double* x_dev, int hsel, const double** K0, const double** V0, cudaStream_t st) {
+  SmallParams p;
+  int rc = small_setup(h, x_dev, 1, hsel, p);
+  if (rc) return rc;
+  small_kstar_kernel<false><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
+  BOPL_LAUNCH_CHECK(h, "small_kstar_kernel");
+  launch_small_gemv<true>(p, h->n, h->m, st);
+  BOPL_LAUNCH_CHECK(h, "small_gemv_kernel<Linv>");
+  *K0 = p.K;
+  *V0 = p.V;
+  return BOPL_OK;
+}
+
 static int launch_posterior_grad_small(bopl_handle* h, const double* Xc, int N, int hsel, double* dmean, double* dvar,
                                        cudaStream_t st) {
   SmallParams p;

@@ -20,9 +20,11 @@ class GPState(object):
     Linv (m,H,n,n) = L^-1 (dtrtri) or None — enables the small-batch matrix-vector path.
     Field map from the reference's live objects: SURVEY.md §7.1-10."""
 
-    def __init__(self, kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv=None, Linv=None):
+    def __init__(self, kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv=None, Linv=None, Y=None):
         self.X = np.ascontiguousarray(X, dtype=np.float64)
         self.n, self.d = self.X.shape
+        # raw targets (m,n) when known: needed only to start a Thompson sample path (Engine.path_begin)
+        self.Y = None if Y is None else np.ascontiguousarray(np.asarray(Y, dtype=np.float64).reshape(-1, self.n))
         self.variance = np.ascontiguousarray(variance, dtype=np.float64)
         self.m, self.H = self.variance.shape
         self.kinds = np.asarray(kinds).reshape(self.m, self.H)
@@ -139,7 +141,7 @@ class Engine(object):
             jitter = base * (10.0 ** tries)
             tries += 1
         self._check(rc)
-        state = GPState(kinds, X, lengthscale, variance, noise, np.repeat(Ym.mean(axis=1)[:, None], H, axis=1), None, None)
+        state = GPState(kinds, X, lengthscale, variance, noise, np.repeat(Ym.mean(axis=1)[:, None], H, axis=1), None, None, Y=Ym)
         state.on_device = True
         state.has_winv, state.has_linv = bool(want_winv), bool(want_linv)
         state.logdet, state.jitter = logdet, jitter
@@ -302,6 +304,34 @@ class Engine(object):
         self._check(self.lib.bopl_uei_grad_host(self.h, ptr(Xc), N, ptr(Z), Z.shape[0], UTILITY_KINDS[kind], ptr(theta), Lt, p,
                                                 ptr(wts), ptr(best), nH, ptr(acq), ptr(dacq)))
         return acq, dacq
+
+    # ------------------------------------------------------------------ Thompson sample path (uTS.py:40-50)
+    def path_begin(self, hsel=0, Y=None, capacity=640):
+        """Start a posterior sample path on hyper-sample `hsel` (`bopl_path_begin`).  Y (m,n): the raw targets of the
+        loaded model (default: the ones the state carries)."""
+        Y = self.state.Y if Y is None else np.ascontiguousarray(np.asarray(Y, dtype=np.float64).reshape(self.m, self.n))
+        if Y is None:
+            raise BoplError(-3, "the loaded GPState carries no targets; pass Y")
+        self._check(self.lib.bopl_path_begin(self.h, int(hsel), int(capacity), ctypes.c_void_p(Y.ctypes.data)))
+
+    def path_eval(self, x, z):
+        """One evaluation of the sample path at x (d,) with the caller's standard-normal draws z (m,): returns
+        (y, mean, var), each (m,); (x, y) joins the path (`bopl_path_eval_host`)."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        z = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(-1))
+        if x.size != self.d or z.size != self.m:
+            raise ValueError("x must have %d entries and z %d" % (self.d, self.m))
+        out = np.empty((3, self.m))
+        ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self._check(self.lib.bopl_path_eval_host(self.h, ptr(x), ptr(z), ptr(out[0]), ptr(out[1]), ptr(out[2])))
+        return out[0], out[1], out[2]
+
+    @property
+    def path_length(self):
+        return int(self.lib.bopl_path_length(self.h))
+
+    def path_end(self):
+        self._check(self.lib.bopl_path_end(self.h))
 
     # ------------------------------------------------------------------ host-buffer path (the reference-facing call)
     def uei_host(self, Xc, Z, kind, theta, wts, best, nH, k=0, index_offset=0, want_acq=True, out=None):

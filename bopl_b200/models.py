@@ -106,7 +106,8 @@ def state_from_hyperparameters(X, Y, kinds, variance, lengthscale, noise, want_w
                 Winv[j, h] = Wj
             if want_linv:
                 Linv[j, h] = inverse_factor(Lj)
-    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv)
+    Ym = np.stack([np.asarray(Y[j], dtype=np.float64).reshape(n) for j in range(m)])
+    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv, Y=Ym)
 
 
 def state_from_reference_model(ref_model, want_winv=True):
@@ -138,7 +139,10 @@ def state_from_reference_model(ref_model, want_winv=True):
             if want_winv:
                 Winv[j, h] = np.asarray(g.posterior.woodbury_inv, dtype=np.float64).reshape(n, n)
     Linv = np.stack([np.stack([inverse_factor(L[j, h]) for h in range(H)]) for j in range(m)])
-    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv)
+    Y = None
+    if all(getattr(insts[j][0], "Y", None) is not None for j in range(m)):
+        Y = np.stack([np.asarray(insts[j][0].Y, dtype=np.float64).reshape(n) for j in range(m)])
+    return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv, Y=Y)
 
 
 # ------------------------------------------------------------------------------------------- the drop-in class
@@ -294,6 +298,12 @@ class MultiOutputGP(object):
     def posterior_variance_gradient(self, X):                                      # multi_outputGP.py:237-246
         _, dvar = self.engine.posterior_grad_dev(self._x(X), self._h, want_mean=False)
         return dvar.cpu().numpy()
+
+    def get_copy_of_model_sample(self):                                            # multi_outputGP.py:286-290
+        """One view per attribute onto a fresh device-side posterior sample path under hyper-sample 0
+        (gpmodel.py:167-168 copies `model_instances[0]`); see `bopl_b200.sampling_policies.SamplePath`."""
+        from .sampling_policies import SamplePath
+        return SamplePath(self).attributes
 
     def get_model_parameters(self):                                                # multi_outputGP.py:268-276
         s = self.state

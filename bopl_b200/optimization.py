@@ -63,10 +63,103 @@ class OptLbfgs(object):
         return np.atleast_2d(res[0]), np.atleast_2d(res[1])
 
 
+def cma_es_minimize(f, x0, sigma0, lower, upper, maxfevals=1000, rng=None, tolfun=1e-11, tolx=1e-11):
+    """(mu/mu_w, lambda)-CMA-ES with the default strategy parameters of Hansen's tutorial ("The CMA Evolution Strategy: A
+    Tutorial", 2016, Table 1 / Algorithm 1): lambda = 4 + floor(3 ln d), log-rank weights, cumulative step-size
+    adaptation, rank-one + rank-mu covariance update, eigen-decomposition refreshed lazily.  Box bounds: candidates are
+    sampled unconstrained, EVALUATED at their projection onto the box, and ranked with a quadratic distance penalty.
+    This stands in for `cma.fmin(f, x0, 0.6, {"bounds": ..., "maxfevals": ...})` (pycma, absent from this image; used by
+    GPyOpt/optimization/optimizer.py:229-261) — same algorithm family and budget, not the same random stream."""
+    rng = np.random if rng is None else rng
+    x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
+    lower, upper = np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64)
+    d = x0.size
+    lam = 4 + int(3 * np.log(d))
+    mu = lam // 2
+    w = np.log(mu + 0.5) - np.log(np.arange(1, mu + 1))
+    w /= w.sum()
+    mueff = 1.0 / np.sum(w ** 2)
+    cc = (4 + mueff / d) / (d + 4 + 2 * mueff / d)
+    cs = (mueff + 2) / (d + mueff + 5)
+    c1 = 2 / ((d + 1.3) ** 2 + mueff)
+    cmu = min(1 - c1, 2 * (mueff - 2 + 1 / mueff) / ((d + 2) ** 2 + mueff))
+    damps = 1 + 2 * max(0.0, np.sqrt((mueff - 1) / (d + 1)) - 1) + cs
+    chiN = np.sqrt(d) * (1 - 1 / (4.0 * d) + 1 / (21.0 * d * d))
+    mean, sigma = np.clip(x0, lower, upper), float(sigma0)
+    pc, ps = np.zeros(d), np.zeros(d)
+    B, D, C = np.eye(d), np.ones(d), np.eye(d)
+    invsqrtC = np.eye(d)
+    eigeneval, counteval = 0, 0
+    best_x, best_f = mean.copy(), np.inf
+    scale = float(np.mean(upper - lower)) if np.all(np.isfinite(upper - lower)) else 1.0
+    while counteval < maxfevals:
+        k = min(lam, maxfevals - counteval)
+        arz = rng.standard_normal((k, d))
+        ary = arz @ (B * D).T
+        arx = mean + sigma * ary
+        feas = np.clip(arx, lower, upper)
+        fit = np.empty(k)
+        for i in range(k):
+            fit[i] = float(np.squeeze(f(feas[i])))
+            if fit[i] < best_f:
+                best_f, best_x = fit[i], feas[i].copy()
+        counteval += k
+        if k < lam:
+            break
+        spread = max(float(np.max(fit) - np.min(fit)), 1e-12)
+        pen = fit + spread * np.sum(((arx - feas) / scale) ** 2, axis=1)
+        idx = np.argsort(pen, kind='stable')[:mu]
+        old = mean
+        mean = w @ arx[idx]
+        ymean = (mean - old) / sigma
+        ps = (1 - cs) * ps + np.sqrt(cs * (2 - cs) * mueff) * (invsqrtC @ ymean)
+        hsig = np.linalg.norm(ps) / np.sqrt(1 - (1 - cs) ** (2.0 * counteval / lam)) / chiN < 1.4 + 2.0 / (d + 1)
+        pc = (1 - cc) * pc + hsig * np.sqrt(cc * (2 - cc) * mueff) * ymean
+        artmp = ary[idx]
+        C = (1 - c1 - cmu) * C + c1 * (np.outer(pc, pc) + (1 - hsig) * cc * (2 - cc) * C) + cmu * (artmp.T * w) @ artmp
+        sigma *= np.exp((cs / damps) * (np.linalg.norm(ps) / chiN - 1))
+        if counteval - eigeneval > lam / (c1 + cmu) / d / 10.0:
+            eigeneval = counteval
+            C = np.triu(C) + np.triu(C, 1).T
+            Dsq, B = np.linalg.eigh(C)
+            D = np.sqrt(np.maximum(Dsq, 1e-300))
+            invsqrtC = (B / D) @ B.T
+        if spread < tolfun and sigma * np.max(D) < tolx:
+            break
+    return best_x, best_f
+
+
+class OptCma(object):
+    """GPyOpt/optimization/optimizer.py:229-261: `cma.fmin(f, x0, 0.6, bounds, maxfevals)`; pycma when importable, else the
+    restatement above."""
+
+    def __init__(self, bounds, maxiter=1000):
+        self.bounds = bounds
+        self.maxiter = maxiter
+
+    def optimize(self, x0, f=None, df=None, f_df=None, maxfevals=1000):
+        if len(self.bounds) == 1:
+            raise IndexError("CMA does not work in problems of dimension 1.")
+        lB, uB = np.asarray(self.bounds)[:, 0], np.asarray(self.bounds)[:, 1]
+        x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
+        try:
+            import cma
+        except ImportError:
+            x, _ = cma_es_minimize(lambda x: f(np.array([x])), x0, 0.6, lB, uB, maxfevals=maxfevals)
+        else:
+            x = cma.fmin(lambda x: float(np.squeeze(f(np.array([x])))), x0, 0.6,
+                         options={"bounds": [lB, uB], "verbose": -1, 'maxfevals': maxfevals})[0]
+        return np.atleast_2d(x), f(np.atleast_2d(x))
+
+
 def choose_optimizer(optimizer_name, bounds):
-    if optimizer_name != 'lbfgs':
-        raise NotImplementedError("only 'lbfgs' is supported (DIRECT / CMA are host-side options of the reference)")
-    return OptLbfgs(bounds)
+    """GPyOpt/optimization/optimizer.py:417-441 ('lbfgs' and 'CMA': the two the BOPL experiments use)."""
+    if optimizer_name == 'lbfgs':
+        return OptLbfgs(bounds)
+    if optimizer_name == 'CMA':
+        return OptCma(bounds)
+    raise NotImplementedError("optimizer %r: only 'lbfgs' and 'CMA' are provided (DIRECT / sgd / adam are host-side options "
+                              "of the reference that no BOPL experiment selects)" % (optimizer_name,))
 
 
 def _round_optimum(space, x):
@@ -75,10 +168,11 @@ def _round_optimum(space, x):
     return np.clip(np.atleast_2d(x), b[:, 0], b[:, 1])
 
 
-def apply_optimizer(optimizer, x0, f, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None):
+def apply_optimizer(optimizer, x0, f, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None,
+                    verbose=False, maxfevals=1000):
     """optimizer.py:264-302 without context / duplicate managers."""
     x0 = np.atleast_2d(x0)
-    optimized_x, _ = optimizer.optimize(x0, f, df, f_df)
+    optimized_x, _ = optimizer.optimize(x0, f, df, f_df, maxfevals=maxfevals)
     x = _round_optimum(space, optimized_x) if space is not None else np.atleast_2d(optimized_x)
     return x, f(x)
 

@@ -209,6 +209,28 @@ int bopl_uei_grad_host(bopl_handle* h, const double* Xc_h, int N, const double* 
                        const double* theta_h, int Lt, int p, const double* wts_h, const double* best_h, int nH,
                        double* acq_h, double* dacq_h);
 
+/* ---- utility Thompson sampling: one posterior sample path, grown point by point -------------------------------------
+ * Replaces the objective of sampling_policies/uTS.py:40-50.  There, every evaluation draws f(x) from a copy of each
+ * attribute's GP (models/multi_outputGP.py:286-290 -> GPyOpt/models/gpmodel.py:167-168: hyper-sample 0), appends the draw
+ * to the copy's data and re-fits it (GPy/core/gp.py:191-227 set_XY: normaliser mean over ALL targets, Ky, dpotrf, dpotrs —
+ * O((n+t)^3) per evaluation), so that later draws are conditioned on earlier ones.  Here the factor is GROWN by one row per
+ * evaluation (rank-1 append, matrix-vector work only) and all m attributes advance in the same launches.
+ *
+ * bopl_path_begin   starts a path on hyper-sample hsel.  Y_h [m*n] HOST: the raw targets the model was fitted to.
+ *                   capacity: expected number of evaluations (buffers double when exceeded; <= 0 -> 256).
+ *                   Needs the inverse factor (Linv_h of bopl_set_model / want_linv of bopl_fit_model).
+ * bopl_path_eval_host  one evaluation at x_h [d] (HOST) with the caller's standard-normal draws z_h [m] (common random
+ *                   numbers: nothing is drawn on the device): mean_j, var_j = posterior at x given the data AND the path so
+ *                   far (GPy/core/gp.py:833-857 `posterior_samples_f(x, size=1, full_cov=True)`: raw variance, no
+ *                   likelihood noise), y_j = mean_j + sqrt(var_j) z_j, then (x, y) joins the path.  y_h [m]; mean_h,
+ *                   var_h [m] may be NULL.  Returns BOPL_ERR_NUMERIC (and drops the path) if the grown covariance is not
+ *                   positive definite.
+ * bopl_path_length  evaluations so far, -1 without a path.   bopl_path_end  frees the path (also done by bopl_set_model). */
+int bopl_path_begin(bopl_handle* h, int hsel, int capacity, const double* Y_h);
+int bopl_path_eval_host(bopl_handle* h, const double* x_h, const double* z_h, double* y_h, double* mean_h, double* var_h);
+int bopl_path_length(const bopl_handle* h);
+int bopl_path_end(bopl_handle* h);
+
 /* Number of kernel launches issued through this handle since creation (bench.py reports the delta). */
 long long bopl_launch_count(const bopl_handle* h);
 

@@ -149,6 +149,7 @@ class ExactGP(object):
             self.lengthscale = np.ones(d) * self.lengthscale
         self.ARD = ARD
         self.noise = float(noise)
+        self.Y = Y
         self.ymean = float(Y.mean(0)[0]) if normalizer else 0.0
         Yn = Y - self.ymean
         K = kern_K(kind, self.variance, self.lengthscale, self.X, None, ARD)

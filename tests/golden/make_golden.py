@@ -403,7 +403,125 @@ def main_marginal():
         print("wrote marginal_%s.npz  value range [%.3e, %.3e]" % (name, out["f_0"].min(), out["f_0"].max()))
 
 
+THOMPSON_CASES = [("dtlz1a_linear", dict(N=4, n=30, n_w=2, L=4, H=2), "test_dtlz1a_linear.py"),
+                  ("dtlz2a_quad", dict(N=4, n=30, n_w=2, L=8, H=2), "test_dtlz2a_quad.py"),
+                  ("vlmop3_exp", dict(N=4, n=30, n_w=2, L=4, H=2), "test_vlmop3_exp.py")]
+
+
+def main_thompson(T=14):
+    """The objective closure of the reference's uTS.suggest_sample (sampling_policies/uTS.py:27-57), executed from the
+    reference's own file: `apply_optimizer` is replaced by a recorder that calls the closure on a fixed sequence of points
+    (one of them repeated, so the path revisits a point it already holds).  The per-attribute GP copies are the reference's
+    `GP.posterior_samples_f` / `GP.set_XY` (method source compiled unchanged; `update_model(True)` runs the first statement of
+    `parameters_changed`, gp.py:254 — the inference; the gradient plumbing after it needs paramz and has no effect on the
+    path).  np.random.multivariate_normal is wrapped to record the (mean, cov, draw) of every call."""
+    import copy
+    from bopl_b200.synthetic import make_problem
+    R = build_reference()
+    gns = dict(np=np, ObsAr=lambda a: np.asarray(a), VariationalPosterior=type("VariationalPosterior", (object,), {}))
+    gp_extra = harvest_methods(os.path.join(GPY, "core/gp.py"), "GP", ["posterior_samples_f", "set_XY"], gns)
+
+    def update_model(self, flag):                                                   # gp.py:254
+        if flag:
+            self.posterior, self._log_marginal_likelihood, self.grad_dict = R.inference(
+                None, self.kern, self.X, self.likelihood, self.Y_normalized, None, None)
+    body = dict(R.GP.__dict__)
+    body = {k: v for k, v in body.items() if not k.startswith("__")}
+    body.update(gp_extra)
+    body.update(update_model=update_model, output_dim=1, parameters=(),
+                _predictive_variable=property(lambda self: self.X))                # gp.py:187-189
+    RefGPPath = type("RefGPPath", (object,), body)
+    gm_copy = harvest_methods(os.path.join(GPYOPT, "models/gpmodel.py"), "GPModel", ["get_copy_of_model_sample"],
+                              dict(np=np, deepcopy=copy.deepcopy))
+    mo_copy = harvest_methods(os.path.join(REF, "bopl/models/multi_outputGP.py"), "MultiOutputGP", ["get_copy_of_model_sample"],
+                              dict(np=np))
+    GPModelP = type("RefGPModelP", (R.GPModel,), gm_copy)
+    MOP = type("RefMultiOutputGPP", (R.MultiOutputGP,), mo_copy)
+
+    # --- the reference's uTS module, plumbing imports stubbed
+    _pkg("sampling_policies")
+    _load("sampling_policies.base", os.path.join(REF, "bopl/sampling_policies/base.py"))
+    _pkg("optimization_services")
+    ao = types.ModuleType("optimization_services.acquisition_optimizer")
+    ao.ContextManager = lambda space, context=None: types.SimpleNamespace(noncontext_bounds=space.get_bounds())
+    sys.modules["optimization_services.acquisition_optimizer"] = ao
+    for name in ["aux_software", "aux_software.GPyOpt", "aux_software.GPyOpt.optimization"]:
+        if name not in sys.modules:
+            _pkg(name)
+    ed = types.ModuleType("aux_software.GPyOpt.experiment_design")
+    sys.modules["aux_software.GPyOpt.experiment_design"] = ed
+    om = types.ModuleType("aux_software.GPyOpt.optimization.optimizer")
+    sys.modules["aux_software.GPyOpt.optimization.optimizer"] = om
+    rec = {}
+
+    def apply_optimizer(optimizer, x0, f=None, context_manager=None, space=None, maxfevals=None, **k):
+        rec["maxfevals"] = maxfevals
+        rec["fvals"] = np.array([np.asarray(f(x)).reshape(-1)[0] for x in rec["Xseq"]])
+        return np.atleast_2d(rec["Xseq"][-1]), None
+    om.apply_optimizer = apply_optimizer
+    om.choose_optimizer = lambda name, bounds: None
+    ed.initial_design = lambda kind, space, n: np.atleast_2d(rec["Xseq"][0])
+    uTS = _load("ref_uTS", os.path.join(REF, "bopl/sampling_policies/uTS.py")).uTS
+
+    for name, kw, script in THOMPSON_CASES:
+        p = make_problem(name, **kw)
+        outs = []
+        for j in range(p["m"]):
+            insts = []
+            for h in range(p["H"]):
+                g = RefGPPath()
+                g.kern = R.make_kern(p["kinds"][j], p["variance"][j, h], p["lengthscale"][j, h], p["d"])
+                g.likelihood = R.Gaussian()
+                g.likelihood.variance = np.array([p["noise"][j, h]])
+                g.mean_function = None
+                g.normalizer = R.Standardize()
+                g.X = p["X"].copy()
+                g.set_XY(p["X"].copy(), p["Y"][j].reshape(-1, 1).copy())           # gp.py:52-62 + 247-260 through the real set_XY
+                insts.append(g)
+            gm = GPModelP()
+            gm.model_instances = insts
+            gm.model = insts[0]
+            outs.append(gm)
+        mo = MOP()
+        mo.output, mo.output_dim, mo.n_samples, mo.name = outs, p["m"], p["H"], "multi-output GP"
+        func, grad = R.exp_utils(script, p["m"])
+        theta = p["theta"]
+        dist = R.UtilityDistribution(prior_sample_generator=lambda n_s, seed=None: theta[:n_s], utility_func=func,
+                                     use_full_support=False)
+        util = R.Utility(func=func, gradient=grad, parameter_distribution=dist)
+        space = types.SimpleNamespace(get_bounds=lambda: [(p["lo"], p["hi"])] * p["d"])
+        rs = np.random.RandomState(99)
+        Xseq = rs.uniform(p["lo"], p["hi"], size=(T, p["d"]))
+        Xseq[9] = Xseq[3]                                                           # a revisited point
+        rec["Xseq"] = Xseq
+        calls = []
+        real_mvn = np.random.multivariate_normal
+
+        def mvn(mean, cov, size=None):
+            out = real_mvn(mean, cov, size)
+            calls.append((float(np.asarray(mean).reshape(-1)[0]), float(np.asarray(cov).reshape(-1)[0]),
+                          float(np.asarray(out).reshape(-1)[0])))
+            return out
+        np.random.seed(4321)
+        np.random.multivariate_normal = mvn
+        try:
+            policy = uTS(mo, space, optimizer="CMA", utility=util)
+            suggested = policy.suggest_sample()
+        finally:
+            np.random.multivariate_normal = real_mvn
+        c = np.array(calls).reshape(T, p["m"], 3)
+        out = dict(name=name, acq="uTS", n=kw["n"], H=kw["H"], seed=4321, Xseq=Xseq, theta=theta[:1], mean=c[:, :, 0],
+                   var=c[:, :, 1], y=c[:, :, 2], fvals=rec["fvals"], suggested=suggested, maxfevals=rec["maxfevals"],
+                   X_aux=policy.X_aux, Y_aux=np.stack([np.asarray(y)[:, 0] for y in policy.Y_aux]))
+        np.savez(os.path.join(HERE, "uTS_%s.npz" % name), **out)
+        print("wrote uTS_%s.npz  fvals [%.3e, %.3e]  min var %.3e" % (name, out["fvals"].min(), out["fvals"].max(), c[:, :, 1].min()))
+
+
 if __name__ == "__main__":
-    main()
-    main_constrained()
-    main_marginal()
+    if len(sys.argv) > 1:
+        {"main": main, "constrained": main_constrained, "marginal": main_marginal, "thompson": main_thompson}[sys.argv[1]]()
+    else:
+        main()
+        main_constrained()
+        main_marginal()
+        main_thompson()

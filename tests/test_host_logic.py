@@ -292,3 +292,55 @@ def test_lockstep_hyperparameter_inference_equals_per_attribute_runs():
         assert np.allclose(v[j], v1, rtol=1e-7) and np.allclose(l[j], l1, rtol=1e-7) and np.allclose(s[j], s1, rtol=1e-7)
     # one batched call per leap-frog step, not one per attribute: (6 + 3*2) HMC iterations x 4 steps + 1, plus the MAP steps
     assert HostStandIn.calls < 12 * 4 + 1 + 200
+
+
+def test_cma_es_restatement_finds_box_constrained_optima():
+    """`OptCma` (GPyOpt/optimization/optimizer.py:229-261) without pycma: interior optimum and optimum on the boundary."""
+    from bopl_b200.optimization import OptCma, choose_optimizer, cma_es_minimize
+    rs = np.random.RandomState(0)
+    x, fx = cma_es_minimize(lambda x: float(np.sum((x - 0.3) ** 2)), np.full(5, 0.9), 0.6, np.zeros(5), np.ones(5), maxfevals=800, rng=rs)
+    assert np.allclose(x, 0.3, atol=1e-3) and fx < 1e-5
+    x, fx = cma_es_minimize(lambda x: float(np.sum((x + 0.3) ** 2)), np.full(3, 0.9), 0.6, np.zeros(3), np.ones(3), maxfevals=600, rng=rs)
+    assert np.allclose(x, 0.0, atol=1e-6)
+    calls = []
+
+    def f(X):
+        calls.append(np.array(X))
+        return np.atleast_1d(np.sum((np.atleast_2d(X) - 0.5) ** 2))
+    np.random.seed(1)
+    opt = choose_optimizer('CMA', [(0.0, 1.0)] * 4)
+    assert isinstance(opt, OptCma)
+    x, fx = opt.optimize(np.full((1, 4), 0.1), f=f, maxfevals=200)
+    assert x.shape == (1, 4) and len(calls) <= 201 and all(c.shape == (1, 4) for c in calls)      # budget respected, 2-D calls
+    assert all(np.all(c >= 0) and np.all(c <= 1) for c in calls)                                  # evaluated inside the box only
+    with pytest.raises(IndexError):
+        OptCma([(0.0, 1.0)]).optimize(np.zeros(1), f=f)
+    with pytest.raises(NotImplementedError):
+        choose_optimizer('DIRECT', [(0.0, 1.0)] * 2)
+
+
+def test_sampling_policies_surface():
+    """Random / AcquisitionFunction policies (sampling_policies/Random.py, AcquisitionFunction.py) on host-only stand-ins."""
+    from bopl_b200.anchor_points import BoxSpace
+    from bopl_b200.sampling_policies import AcquisitionFunction, Random, SamplingPolicyBase, uTS
+    space = BoxSpace([(0.0, 2.0)] * 3)
+    x = Random(None, space).suggest_sample()
+    assert x.shape == (1, 3) and np.all(x >= 0) and np.all(x <= 2)
+    with pytest.raises(NotImplementedError):
+        SamplingPolicyBase().suggest_sample()
+
+    class Acq(object):
+        def __init__(self):
+            self.optimizer = type("O", (), {})()
+            self.updated = 0
+
+        def update_samples(self):
+            self.updated += 1
+
+        def optimize(self, duplicate_manager=None):
+            return np.array([[1.0, 1.0, 1.0]]), np.array([[0.5]])
+    acq = Acq()
+    pol = AcquisitionFunction(None, space, acq)
+    assert np.array_equal(pol.suggest_sample(), [[1.0, 1.0, 1.0]]) and acq.updated == 1
+    assert acq.optimizer.context_manager.noncontext_bounds == space.get_bounds()
+    assert uTS.analytical_gradient_prediction and AcquisitionFunction.analytical_gradient_prediction

@@ -179,6 +179,26 @@ def test_oracle_against_reference_generated_golden(fname):
     """Fixtures made by running the reference's own uEI.py / uEI_affine.py code (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, fname), allow_pickle=False)
     name, H = str(g["name"]), int(g["H"])
+    if str(g["acq"]) == "uTS":
+        # the reference's own uTS.suggest_sample closure (uTS.py:40-50) on its own GP.posterior_samples_f / set_XY
+        from oracle.thompson import SamplePathOracle
+        p = make_problem(name, N=4, n=int(g["n"]), n_w=2, L=len(g["theta"]) if name != "dtlz2a_quad" else 8, H=H)
+        om = oracle_model(p)
+        func, _ = utilities.get(p["utility"], p["m"])
+        sp = SamplePathOracle([om.gps[j][0] for j in range(p["m"])])
+        np.random.seed(int(g["seed"]))                               # same global stream as the reference run
+        for t, x in enumerate(g["Xseq"]):
+            mean_before = [gp.ymean for gp in sp.gps]
+            y, mu, var = sp.evaluate(x)
+            sc = max(np.abs(g["mean"]).max(), 1.0)
+            assert np.allclose(mu, g["mean"][t], rtol=1e-9, atol=1e-10 * sc), (t, mu, g["mean"][t])
+            assert np.allclose(var, g["var"][t], rtol=1e-7, atol=1e-11 * p["variance"][:, 0].max()), (t, var, g["var"][t])
+            assert np.allclose(y, g["y"][t], rtol=1e-9, atol=1e-10 * sc), (t, y, g["y"][t])
+            f = -np.atleast_1d(func(np.squeeze(y), g["theta"]))
+            assert np.allclose(f, g["fvals"][t], rtol=1e-8), (t, f, g["fvals"][t])
+            assert all(gp.ymean != mb for gp, mb in zip(sp.gps, mean_before))      # the normaliser mean moves with the path
+        assert np.allclose(sp.X_aux, g["X_aux"]) and np.allclose(np.stack([y[:, 0] for y in sp.Y_aux]), g["Y_aux"], rtol=1e-9, atol=1e-9)
+        return
     if str(g["acq"]) == "marginal":
         p = make_problem(name, N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=H)
         assert np.array_equal(p["Xc"], g["Xc"]) and np.array_equal(p["theta"], g["theta"])
