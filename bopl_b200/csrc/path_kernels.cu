@@ -179,21 +179,34 @@ __global__ void __launch_bounds__(256) path_finish_kernel(PathParams p) {
   p.out[2 * p.m + j] = var;
 }
 
-// New row of Cinv (columns 0..t), new row of B (= v0), the point itself.  grid (ceil((t+1)/256) + ceil(n/256), m).
+// New row of Cinv (columns 0..t), new row of B (= v0), the point itself.  grid (ceil((t+1)/32) + ceil(n/256), m).
+// A Cinv block owns 32 columns (one per lane, 256-byte coalesced row segments); its 8 warps take the rows i = k0 + w, k0 + w + 8, ...
+// and the 8 partial sums are added in a fixed order.
 __global__ void __launch_bounds__(256) path_append_kernel(PathParams p) {
+  __shared__ double part[8][32];
   const int j = blockIdx.y, n = p.n, t = p.t;
   const PathAttr at = p.attrs[j];
-  const int cblocks = (t + 1 + 255) / 256;
+  const int cblocks = (t + 1 + 31) / 32;
   if ((int)blockIdx.x < cblocks) {
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    const double l = p.scal[j * 8 + 3];
-    if (k < t) {
-      const double* u = p.u + (size_t)j * p.cap;
-      double s = 0.0;
-      for (int i = k; i < t; ++i) s = fma(u[i], at.Cinv[(size_t)i * p.cap + k], s);
-      at.Cinv[(size_t)t * p.cap + k] = -s / l;
-    } else if (k == t) {
-      at.Cinv[(size_t)t * p.cap + t] = 1.0 / l;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * 32, k = k0 + lane;
+    const double* u = p.u + (size_t)j * p.cap;
+    double s = 0.0;
+    if (k < t)
+      for (int i = k0 + warp; i < t; i += 8)
+        if (i >= k) s = fma(u[i], at.Cinv[(size_t)i * p.cap + k], s);
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+      const double l = p.scal[j * 8 + 3];
+      if (k < t) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += part[w][lane];
+        at.Cinv[(size_t)t * p.cap + k] = -a / l;
+      } else if (k == t) {
+        at.Cinv[(size_t)t * p.cap + t] = 1.0 / l;
+      }
     }
     if (j == 0 && blockIdx.x == 0 && threadIdx.x < p.d) p.Xp[(size_t)t * p.d + threadIdx.x] = p.x[threadIdx.x];
   } else {
@@ -367,7 +380,7 @@ int bopl_path_eval_host(bopl_handle* h, const double* x_h, const double* z_h, do
   }
   path_finish_kernel<<<m, 256, 0, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "path_finish_kernel");
-  path_append_kernel<<<dim3((t + 1 + 255) / 256 + (n + 255) / 256, m), 256, 0, st>>>(p);
+  path_append_kernel<<<dim3((t + 1 + 31) / 32 + (n + 255) / 256, m), 256, 0, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "path_append_kernel");
   BOPL_CUDA(h, cudaMemcpyAsync(ps->io_pin + d + m, ps->io_dev + d + m, (size_t)3 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
   BOPL_CUDA(h, cudaMemcpyAsync(ps->info_pin, ps->info_dev, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
