@@ -14,7 +14,7 @@ from .anchor_points import ObjectiveAnchorPointsGenerator, BoxSpace
 
 def __getattr__(name):
     # engine / models / acquisition import torch lazily through these names
-    if name in ("MultiOutputGP", "state_from_hyperparameters", "state_from_reference_model", "fit_exact_gp"):
+    if name in ("MultiOutputGP", "BasicModel", "state_from_hyperparameters", "state_from_reference_model", "fit_exact_gp"):
         from . import models
         return getattr(models, name)
     if name in ("uEI", "uEI_affine", "uEI_constrained", "AcquisitionBase"):
@@ -23,6 +23,9 @@ def __getattr__(name):
     if name in ("AcquisitionOptimizer", "OptLbfgs", "apply_optimizer"):
         from . import optimization
         return getattr(optimization, name)
+    if name in ("AcquisitionFunction", "Random", "uTS", "ParEGO", "SamplePath", "Sequential", "chebyshev_scalarization"):
+        from . import sampling_policies
+        return getattr(sampling_policies, name)
     if name in ("Engine", "GPState"):
         from . import engine
         return getattr(engine, name)

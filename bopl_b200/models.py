@@ -145,6 +145,34 @@ def state_from_reference_model(ref_model, want_winv=True):
     return GPState(kinds, X, lengthscale, variance, noise, ymean, L, alpha, Winv, Linv, Y=Y)
 
 
+class BasicModel(object):
+    """models/basic_model.py:6-44: only stores the evaluations (the model ParEGO / Random are paired with)."""
+    analytical_gradient_prediction = True
+
+    def __init__(self, output_dim=None, X=None, Y=None):
+        self.output_dim, self.X, self.Y = output_dim, X, Y
+        self.name = 'basic model'
+
+    def updateModel(self, X, Y):
+        self.X, self.Y = X, Y
+
+    def get_X(self):
+        return np.copy(self.X)
+
+    def get_Y(self):
+        import copy
+        return copy.deepcopy(self.Y)
+
+    def get_XY(self):
+        return self.get_X(), self.get_Y()
+
+    def get_model_parameters(self):
+        pass
+
+    def get_model_parameters_names(self):
+        pass
+
+
 # ------------------------------------------------------------------------------------------- the drop-in class
 class MultiOutputGP(object):
     """GPU-backed stand-in for `bopl.models.MultiOutputGP` (multi_outputGP.py:9-290)."""

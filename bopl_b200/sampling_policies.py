@@ -1,5 +1,7 @@
 """Sampling policies of `bopl/sampling_policies/` on the GPU engine: `AcquisitionFunction` (AcquisitionFunction.py:7-36),
-`Random` (Random.py:7-26) and utility Thompson sampling `uTS` (uTS.py:12-57).
+`Random` (Random.py:7-26), utility Thompson sampling `uTS` (uTS.py:12-57) and `ParEGO` (ParEGO.py:15-66: a one-attribute
+auxiliary GP on a random Chebyshev scalarisation of the observations, maximised with `uEI_affine` — every piece of it is one
+of the accelerated classes).
 
 uTS maximises the utility of ONE posterior sample path.  The reference grows the path inside its objective: every
 evaluation draws f(x) from a deep copy of each attribute's GP, appends the draw to the copy's data and re-fits the copy
@@ -161,3 +163,53 @@ class uTS(SamplingPolicyBase):                                                  
         finally:
             self.model.engine.path_end()
         return np.atleast_2d(suggested_sample)
+
+
+def chebyshev_scalarization(Y, weight):                                             # others/chebyshev_scalarization.py:3-5
+    tmp = np.multiply(weight, Y.T).T
+    return np.min(tmp, axis=0) + 0.05 * np.sum(Y, axis=0)
+
+
+class ParEGO(SamplingPolicyBase):                                                   # ParEGO.py:15-66
+    """`model` only has to hand out the evaluations (`get_XY`: the reference pairs ParEGO with `BasicModel`)."""
+    analytical_gradient_prediction = True
+
+    def __init__(self, model, space, utility, optimizer='lbfgs', device=0, aux_model_options=None):
+        super(ParEGO, self).__init__(model, space)
+        self.utility = utility
+        self.optimizer = optimizer
+        self.device = device
+        self.aux_model_options = dict(aux_model_options or {})      # e.g. n_samples / fit_options of the auxiliary GP
+        dist = getattr(self.utility, "parameter_distribution", None)
+        self.preference_information = getattr(dist, "preference_information", [])
+
+    def suggest_sample(self, number_of_samples=1):
+        from .acquisition import uEI_affine
+        from .models import MultiOutputGP
+        from .optimization import AcquisitionOptimizer
+        from .utility import Utility, UtilityDistribution
+        X_evaluated, Y_evaluated = self.model.get_XY()
+        self.X_aux, self.Y_aux = X_evaluated, Y_evaluated
+        weight = np.random.dirichlet(np.ones(len(self.Y_aux)))                      # ParEGO.py:43
+        self.Y_aux = np.reshape(self.Y_aux, (len(self.Y_aux), self.Y_aux[0].shape[0]))
+        scalarized_fX = chebyshev_scalarization(self.Y_aux, weight)
+        scalarized_fX = np.reshape(scalarized_fX, (len(scalarized_fX), 1))
+        aux_model = MultiOutputGP(output_dim=1, exact_feval=[True], fixed_hyps=False, device=self.device, **self.aux_model_options)
+
+        def aux_utility_func(y, parameter):
+            return np.dot(parameter, y)
+
+        def aux_utility_gradient(y, parameter):
+            return parameter
+
+        aux_dist = UtilityDistribution(support=np.ones((1, 1)), prob_dist=np.ones((1,)), utility_func=aux_utility_func)
+        aux_utility = Utility(func=aux_utility_func, gradient=aux_utility_gradient, parameter_distribution=aux_dist, affine=True)
+        aux_model.updateModel(self.X_aux, [scalarized_fX])                          # core/bopl.py:428-429
+        aux_optimizer = AcquisitionOptimizer(space=self.space, model=aux_model, utility=aux_utility, optimizer=self.optimizer,
+                                             include_baseline_points=True)
+        aux_acquisition = uEI_affine(aux_model, self.space, optimizer=aux_optimizer, utility=aux_utility)
+        aux_policy = AcquisitionFunction(aux_model, self.space, aux_acquisition, Sequential(aux_acquisition))
+        try:
+            return aux_policy.suggest_sample()                                      # core/bopl.py:430
+        finally:
+            aux_model.engine.close()

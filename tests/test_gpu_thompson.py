@@ -164,3 +164,22 @@ def test_path_on_a_device_fitted_model():
         x, z = rs.uniform(p["lo"], p["hi"], size=p["d"]), rs.standard_normal(p["m"])
         _check_step(t, (path.evaluate(x, z), path.last_mean, path.last_var), sp.evaluate(x, z), float(p["variance"].max()), 16.0)
     gm.engine.path_end()
+
+
+def test_parego_policy_on_the_accelerated_classes():
+    """ParEGO.py:32-66 composed of the GPU-backed MultiOutputGP(1) + uEI_affine + AcquisitionOptimizer(baseline points)."""
+    from bopl_b200 import BasicModel, ParEGO
+    from bopl_b200.anchor_points import BoxSpace
+    from bopl_b200.sampling_policies import chebyshev_scalarization
+    p = make_problem("vlmop3_exp", N=4, n=24, n_w=2, L=4)
+    space = BoxSpace([(p["lo"], p["hi"])] * p["d"])
+    model = BasicModel(output_dim=p["m"])
+    model.updateModel(p["X"], [p["Y"][j][:, None] for j in range(p["m"])])
+    np.random.seed(5)
+    pol = ParEGO(model, space, make_utility(p), aux_model_options=dict(
+        n_samples=2, fit_options=dict(n_burnin=10, subsample_interval=2, leapfrog_steps=5, max_iters=50)))
+    x = pol.suggest_sample()
+    assert x.shape == (1, p["d"]) and np.all(x >= p["lo"]) and np.all(x <= p["hi"])
+    w = np.array([0.2, 0.3, 0.5])
+    Y = np.arange(12.0).reshape(3, 4)
+    assert np.allclose(chebyshev_scalarization(Y, w), np.min(w[:, None] * Y, axis=0) + 0.05 * Y.sum(axis=0))
