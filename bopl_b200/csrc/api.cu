@@ -41,6 +41,7 @@ void free_model(bopl_handle* h) {
   h->has_model = false;
   h->has_winv = false;
   h->has_linv = false;
+  h->has_oz = false;
   h->F_valid = false;
 }
 
@@ -155,6 +156,7 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_TRSM_VARIANT")) h->trsm_variant = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
+  if (const char* v = getenv("BOPL_OZAKI")) h->use_ozaki = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_KEEP_BLOCKS")) h->trsm_keep_blocks = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_L2_HINTS")) h->trsm_l2_hints = atoi(v);
@@ -177,7 +179,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev, h->fit_ws};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev, h->fit_ws, h->oz_scratch};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -261,6 +263,26 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
         return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
       }
     }
+    // int8 digit images for the INT8-tensor-pipe variant (posterior_ozaki.cu): from the un-negated factor
+    signed char* pOzL = nullptr;
+    double *pOzS = nullptr, *pOzD = nullptr;
+    if (h->use_ozaki) {
+      std::vector<signed char> img;
+      std::vector<double> osc;
+      ozaki_prepare(Lp.data(), n_pad, img, osc);
+      const int nb64 = n_pad / 64;
+      std::vector<double> d64((size_t)nb64 * 64 * 64);
+      for (int b = 0; b < nb64; ++b)
+        if (!invert_lower_block(Lp.data() + (size_t)b * 64 * n_pad + (size_t)b * 64, n_pad, 64, d64.data() + (size_t)b * 64 * 64)) {
+          free_model(h);
+          return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
+        }
+      if ((rc = dev_upload(h, img.data(), img.size(), &pOzL)) || (rc = dev_upload(h, osc.data(), osc.size(), &pOzS)) ||
+          (rc = dev_upload(h, d64.data(), d64.size(), &pOzD))) {
+        free_model(h);
+        return rc;
+      }
+    }
     // negate the off-diagonal blocks so that the kernel's update is a pure accumulate: acc += (-L) V
     for (int i = 0; i < n_pad; ++i) {
       const int bi = i / TRSM_BM;
@@ -294,6 +316,9 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       return rc;
     }
     gp.Linv = pLi;
+    gp.OzL = pOzL;
+    gp.OzScale = pOzS;
+    gp.OzDinv = pOzD;
     gp.Lneg = pL;
     gp.Dinv = pD;
     gp.DinvFrag = pF;
@@ -316,6 +341,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   h->gp_dev = gd;
   h->has_winv = Winv_h != nullptr;
   h->has_linv = Linv_h != nullptr;
+  h->has_oz = h->use_ozaki != 0;
   h->has_model = true;
   h->F_valid = false;
   return BOPL_OK;

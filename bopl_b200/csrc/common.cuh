@@ -30,6 +30,9 @@ struct GpDev {
   const double* Winv;    // [n*n] or nullptr
   const double* Linv;    // [n*n] explicit inverse of the Cholesky factor (lower triangular, row-major) or nullptr
   const double* ell;     // [d]
+  const signed char* OzL;   // int8 digit images of the off-diagonal 64x64 blocks (posterior_ozaki.cu) or nullptr
+  const double* OzScale;    // [n_pad] power-of-two row scales of those digits
+  const double* OzDinv;     // [n_pad/64][64][64] inverted 64x64 diagonal blocks
   double variance, noise, ymean;
   int kind;
   int _pad;
@@ -79,6 +82,9 @@ struct bopl_handle {
   void* fit_ws = nullptr; size_t fit_ws_bytes = 0;   // workspace of bopl_log_marginal (factor, inverse, K^-1 of every instance)
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
   void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
+  int use_ozaki = 0;                   // BOPL_OZAKI=1: bopl_set_model also builds the int8 digit images (posterior_ozaki.cu)
+  bool has_oz = false;
+  void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem = 0;
   size_t hsmall_cap = 0;
 };
 
@@ -133,6 +139,9 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st);
 bool trsm_t_fits(int d);
+bool ozaki_available(const bopl_handle* h);
+void ozaki_prepare(const double* Lp, int n_pad, std::vector<signed char>& img, std::vector<double>& scale);
+int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags, cudaStream_t st);
 void pack_dinv_fragments(const double* Dinv_block, double* out);
 void pack_stage_blocks(const double* Xs, const double* alpha, int n_pad, int d, double* out);
 bool use_small_path(const bopl_handle* h, int N);

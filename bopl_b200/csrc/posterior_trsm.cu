@@ -364,6 +364,7 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
                           cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
   if (use_small_path(h, N)) return launch_posterior_small(h, Xc, N, hsel, mean, var, flags, st);
+  if (h->trsm_variant == 4 && ozaki_available(h)) return launch_posterior_ozaki(h, Xc, N, hsel, mean, var, flags, st);
   // default: the candidate-owning kernel; wider inputs (d > 20) do not fit its shared-memory plan -> row-owning form
   if (h->trsm_variant != 1 && h->trsm_variant != 2 && trsm_t_fits(h->d))
     return launch_posterior_trsm_t(h, Xc, N, hsel, mean, var, flags, st);
