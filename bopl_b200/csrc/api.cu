@@ -264,24 +264,17 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       }
     }
     // int8 digit images for the INT8-tensor-pipe variant (posterior_ozaki.cu): from the un-negated factor
-    signed char* pOzL = nullptr;
-    double *pOzS = nullptr, *pOzD = nullptr;
+    std::vector<signed char> oz_img;
+    std::vector<double> oz_scale, oz_d64;
     if (h->use_ozaki) {
-      std::vector<signed char> img;
-      std::vector<double> osc;
-      ozaki_prepare(Lp.data(), n_pad, img, osc);
+      ozaki_prepare(Lp.data(), n_pad, oz_img, oz_scale);
       const int nb64 = n_pad / 64;
-      std::vector<double> d64((size_t)nb64 * 64 * 64);
+      oz_d64.resize((size_t)nb64 * 64 * 64);
       for (int b = 0; b < nb64; ++b)
-        if (!invert_lower_block(Lp.data() + (size_t)b * 64 * n_pad + (size_t)b * 64, n_pad, 64, d64.data() + (size_t)b * 64 * 64)) {
+        if (!invert_lower_block(Lp.data() + (size_t)b * 64 * n_pad + (size_t)b * 64, n_pad, 64, oz_d64.data() + (size_t)b * 64 * 64)) {
           free_model(h);
           return fail(h, BOPL_ERR_INVALID, "Cholesky factor has a non-positive diagonal entry");
         }
-      if ((rc = dev_upload(h, img.data(), img.size(), &pOzL)) || (rc = dev_upload(h, osc.data(), osc.size(), &pOzS)) ||
-          (rc = dev_upload(h, d64.data(), d64.size(), &pOzD))) {
-        free_model(h);
-        return rc;
-      }
     }
     // negate the off-diagonal blocks so that the kernel's update is a pure accumulate: acc += (-L) V
     for (int i = 0; i < n_pad; ++i) {
@@ -297,6 +290,16 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       al[pad + i] = alpha_h[(size_t)g * n + i];
     }
     pack_stage_blocks(Xs.data(), al.data(), n_pad, d, SBlk.data());
+    signed char* pOzL = nullptr;
+    double* pOzS = nullptr;
+    if (h->use_ozaki) {
+      std::vector<double> oz_stage;
+      ozaki_pack_stage(oz_d64.data(), Xs.data(), al.data(), oz_scale.data(), n_pad, d, oz_stage);
+      if ((rc = dev_upload(h, oz_img.data(), oz_img.size(), &pOzL)) || (rc = dev_upload(h, oz_stage.data(), oz_stage.size(), &pOzS))) {
+        free_model(h);
+        return rc;
+      }
+    }
     GpDev gp{};
     double *pL, *pD, *pF, *pX, *pa, *pe, *pS, *pW = nullptr;
     if ((rc = dev_upload(h, Lp.data(), Lp.size(), &pL)) || (rc = dev_upload(h, Dinv.data(), Dinv.size(), &pD)) ||
@@ -317,8 +320,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     }
     gp.Linv = pLi;
     gp.OzL = pOzL;
-    gp.OzScale = pOzS;
-    gp.OzDinv = pOzD;
+    gp.OzStage = pOzS;
     gp.Lneg = pL;
     gp.Dinv = pD;
     gp.DinvFrag = pF;

@@ -31,8 +31,7 @@ struct GpDev {
   const double* Linv;    // [n*n] explicit inverse of the Cholesky factor (lower triangular, row-major) or nullptr
   const double* ell;     // [d]
   const signed char* OzL;   // int8 digit images of the off-diagonal 64x64 blocks (posterior_ozaki.cu) or nullptr
-  const double* OzScale;    // [n_pad] power-of-two row scales of those digits
-  const double* OzDinv;     // [n_pad/64][64][64] inverted 64x64 diagonal blocks
+  const double* OzStage;    // [n_pad/64][...] per 64-row block: Dinv B fragments, scaled training rows^T, alpha, row scales of the digits
   double variance, noise, ymean;
   int kind;
   int _pad;
@@ -141,6 +140,8 @@ int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, d
 bool trsm_t_fits(int d);
 bool ozaki_available(const bopl_handle* h);
 void ozaki_prepare(const double* Lp, int n_pad, std::vector<signed char>& img, std::vector<double>& scale);
+void ozaki_pack_stage(const double* Dinv64, const double* Xs, const double* alpha, const double* scale, int n_pad, int d,
+                      std::vector<double>& out);
 int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags, cudaStream_t st);
 void pack_dinv_fragments(const double* Dinv_block, double* out);
 void pack_stage_blocks(const double* Xs, const double* alpha, int n_pad, int d, double* out);
