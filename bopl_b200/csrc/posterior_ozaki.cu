@@ -50,6 +50,7 @@ struct OzParams {
   double* var;
   signed char* scratch;   // [grid][n_pad/64][VIMG]
   int H, hsel, m, N, d, n_pad, pad, ntiles, flags;
+  int keep_blocks;        // solved blocks below this index are kept in L2 (evict_last), the rest is streamed
 };
 
 // staged per block row: Dinv B fragments, scaled training rows transposed [q][64], alpha[64], row scales[64]
@@ -81,6 +82,11 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 // 16 TMEM lanes x 8 columns: lane l/4 (+8), columns 2 (l%4), 2 (l%4) + 1 — the C-fragment layout of an 8x8 DMMA tile pair
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     if (lane == 0) {
       unsigned gc = 0, brow = 0, sc = 0;   // k-steps issued; block rows whose digits were waited for; staging blocks issued
       const unsigned sb_bytes = (unsigned)SBD * 8;
+      const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
       auto stage_block = [&](const GpDev& g, int i) {
         const unsigned buf = sc & 1;
         if (sc >= 2) mbar_wait(&sb_empty[buf], ((sc >> 1) - 1) & 1);
@@ -138,30 +145,36 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         bulk_g2s(SB + (size_t)buf * SBD, g.OzStage + (size_t)i * SBD, sb_bytes, &sb_full[buf]);
         ++sc;
       };
+      auto load_block = [&](const signed char* Limg, int i, int kb) {      // both k-steps of block (i, kb)
+        const unsigned long long vpol = kb < p.keep_blocks ? pol_keep : pol_stream;
+#pragma unroll 1
+        for (int ks = 0; ks < 2; ++ks) {
+          const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
+          mbar_wait(&empty_bar[st], (use & 1) ^ 1);
+          unsigned char* dst = stage_s + (size_t)st * OSTAGE;
+          mbar_expect_tx(&full_bar[st], OSTAGE);
+          bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
+          bulk_g2s_hint(dst + LHALF, Vpanel + (size_t)kb * VIMG + (size_t)ks * VHALF, VHALF, &full_bar[st], vpol);
+          ++gc;
+        }
+      };
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const GpDev& gp = p.gps[(item / p.ntiles) * p.H + p.hsel];
         const signed char* Limg = gp.OzL;
         if (item == (int)blockIdx.x) stage_block(gp, 0);
         for (int i = 0; i < nb; ++i) {
+          // The staging block of row i+1 reuses the buffer of row i-1, free once that row's diagonal solve is over — which is
+          // before its digits are published: issue it behind the wait for those digits, so that the k-steps of the blocks
+          // kb < i-1 (needing neither) are prefetched while the previous block row is still being solved.
+          for (int kb = 0; kb + 1 < i; ++kb) load_block(Limg, i, kb);
+          if (i > 0) {                        // the newest block: wait until its digits are in the scratch panel
+            mbar_wait(&v_pub, brow & 1);
+            ++brow;
+            asm volatile("fence.proxy.async;\n" ::: "memory");
+          }
           if (i + 1 < nb) stage_block(gp, i + 1);
           else if (item + (int)gridDim.x < nitems) stage_block(p.gps[((item + (int)gridDim.x) / p.ntiles) * p.H + p.hsel], 0);
-          for (int kb = 0; kb < i; ++kb) {
-#pragma unroll 1
-            for (int ks = 0; ks < 2; ++ks) {
-              const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
-              mbar_wait(&empty_bar[st], (use & 1) ^ 1);
-              if (kb == i - 1 && ks == 0) {   // the newest block: wait until its digits are in the scratch panel
-                mbar_wait(&v_pub, brow & 1);
-                ++brow;
-                asm volatile("fence.proxy.async;\n" ::: "memory");
-              }
-              unsigned char* dst = stage_s + (size_t)st * OSTAGE;
-              mbar_expect_tx(&full_bar[st], OSTAGE);
-              bulk_g2s(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st]);
-              bulk_g2s(dst + LHALF, Vpanel + (size_t)kb * VIMG + (size_t)ks * VHALF, VHALF, &full_bar[st]);
-              ++gc;
-            }
-          }
+          if (i > 0) load_block(Limg, i, i - 1);
         }
         mbar_wait(&v_pub, brow & 1);       // the last block row arrives too: keep the phases in step
         ++brow;
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
       const double variance = gp.variance;
       const double vs = exp2(ceil(log2(sqrt(variance))) + 1.0);  // fixed-point scale of V: |V| <= sigma <= vs / 2
       const double to_fix = 140737488355328.0 / vs;              // 2^47 / vs
-      const double from_fix = vs * (1.0 / 16384.0);              // vs 2^-14
+      const double from_fix16 = vs * (1.0 / 1073741824.0);       // vs 2^-14 (digit product weight) 2^-16 (integer Horner)
       const double vmax = 0.5 * vs;
       __syncwarp();
       for (int idx = lane; idx < 16 * d; idx += 32) {
@@ -294,12 +307,16 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             for (int w = 0; w < OS; ++w) tmem_ld_frag(trow + (uint32_t)(w * 64 + nt * 8), a[w]);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             const double2 rs = *reinterpret_cast<const double2*>(scale_s + 8 * nt + 2 * t);
-            const double s0 = -(rs.x * from_fix), s1 = -(rs.y * from_fix);
+            const double s0 = -(rs.x * from_fix16), s1 = -(rs.y * from_fix16);
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-              double h = (double)a[OS - 1][x];
-#pragma unroll
-              for (int w = OS - 2; w >= 0; --w) h = fma(h, 1.0 / 256.0, (double)a[w][x]);
+              // weights 0..2 and 3..5 combined exactly in 64-bit integers (< 2^48), converted by the 1.5 * 2^52 trick (I2F.F64 runs
+              // at a quarter of the DFMA rate), joined by one FMA
+              const long long hi3 = ((long long)a[0][x] << 16) + ((long long)a[1][x] << 8) + (long long)a[2][x];
+              const long long lo3 = ((long long)a[3][x] << 16) + ((long long)a[4][x] << 8) + (long long)a[5][x];
+              const double dh = __longlong_as_double(0x4338000000000000LL + hi3) - 6755399441055744.0;
+              const double dl = __longlong_as_double(0x4338000000000000LL + lo3) - 6755399441055744.0;
+              const double h = fma(dl, 1.0 / 16777216.0, dh);
               acc[x >> 1][nt][x & 1] = fma((x & 1) ? s1 : s0, h, acc[x >> 1][nt][x & 1]);
             }
           }
@@ -391,7 +408,8 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 #pragma unroll
             for (int s = 0; s < OS; ++s) *reinterpret_cast<uint4*>(img + (size_t)s * VPL + (size_t)mi * 128) = make_uint4(plw[s][0], plw[s][1], plw[s][2], plw[s][3]);
           }
-          __threadfence();
+          // generic-proxy stores -> the producer's bulk copies (async proxy): proxy fence, then release through the mbarrier.
+          // (No gpu-scope __threadfence: its CCTL.IVALL / MEMBAR were 48 % of this phase's stall samples.)
           asm volatile("fence.proxy.async;\n" ::: "memory");
         }
         mbar_arrive(&v_pub);
@@ -524,6 +542,17 @@ int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, do
   int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)grid * nb * VIMG);
   if (rc) return rc;
   p.scratch = (signed char*)h->oz_scratch;
+  {
+    // L2 budget as in posterior_trsm_t.cu: the digit image of the running attribute's factor stays resident; of the rest every CTA
+    // keeps the first blocks of its solved panel — the ones re-read most often
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
+    const double limg = (double)nb * (nb - 1) / 2 * LIMG;
+    const double budget = (h->trsm_l2_keep_frac * (double)l2 - 1.5 * limg) / grid;
+    long long blocks = (long long)(budget / (double)VIMG);
+    if (h->trsm_keep_blocks >= 0) blocks = h->trsm_keep_blocks;
+    p.keep_blocks = (int)std::max<long long>(0, std::min<long long>(blocks, nb));
+  }
   const size_t smem = oz_smem_bytes(h->d);
   if (smem > h->oz_attr_smem) {
     BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
