@@ -17,6 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}
+POSTERIOR_KERNELS = {"fp64": 0, "int8": 6, "int8x7": 7}   # bopl_set_posterior_kernel
 VAR_INCLUDE_NOISE = 1
 VAR_CLIP = 2
 ERR_NUMERIC = -5
@@ -26,7 +27,7 @@ SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", 
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
            "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
            "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count", "bopl_fit_model", "bopl_log_marginal",
-           "bopl_get_factor", "bopl_path_begin", "bopl_path_eval_host", "bopl_path_length", "bopl_path_end"]
+           "bopl_get_factor", "bopl_set_posterior_kernel", "bopl_get_posterior_kernel", "bopl_path_begin", "bopl_path_eval_host", "bopl_path_length", "bopl_path_end"]
 
 
 class BoplError(RuntimeError):
@@ -123,6 +124,8 @@ def load():
     lib.bopl_path_length.argtypes = [vp]
     lib.bopl_path_end.argtypes = [vp]
     lib.bopl_launch_count.argtypes = [vp]
+    lib.bopl_set_posterior_kernel.argtypes = [vp, c_int]
+    lib.bopl_get_posterior_kernel.argtypes = [vp]
     lib.bopl_launch_count.restype = c_ll
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError if the library does not export what the header declares

@@ -157,6 +157,15 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
   if (const char* v = getenv("BOPL_OZAKI")) h->use_ozaki = atoi(v);
+  if (const char* v = getenv("BOPL_OZAKI_DIGITS")) h->oz_digits = atoi(v) == 7 ? 7 : 6;
+  if (const char* v = getenv("BOPL_POSTERIOR")) {        // "fp64" (default), "int8" (6 digits), "int8x7"
+    const std::string k(v);
+    if (k == "int8" || k == "int8x7") {
+      h->trsm_variant = 4;
+      h->use_ozaki = 1;
+      h->oz_digits = k == "int8" ? 6 : 7;
+    }
+  }
   if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_KEEP_BLOCKS")) h->trsm_keep_blocks = atoi(v);
   if (const char* v = getenv("BOPL_TRSM_L2_HINTS")) h->trsm_l2_hints = atoi(v);
@@ -198,6 +207,28 @@ int bopl_device_sms(const bopl_handle* h) { return h ? h->sms : 0; }
 const char* bopl_build_info(void) { return "libbopl_b200 sm_100a (compute_100a) fp64 DMMA.8x8x4 " __DATE__; }
 
 long long bopl_launch_count(const bopl_handle* h) { return h ? h->launches : 0; }
+
+int bopl_set_posterior_kernel(bopl_handle* h, int kind) {
+  if (!h) return fail(nullptr, BOPL_ERR_INVALID, "null handle");
+  if (kind != BOPL_POSTERIOR_FP64 && kind != BOPL_POSTERIOR_INT8 && kind != BOPL_POSTERIOR_INT8_7)
+    return fail(h, BOPL_ERR_INVALID, "unknown posterior kernel kind");
+  if (kind != BOPL_POSTERIOR_FP64 && h->has_model && (!h->has_oz || h->oz_digits != kind))
+    return fail(h, BOPL_ERR_STATE, "the loaded model carries no digit images of that width: select the kernel before bopl_set_model / bopl_fit_model");
+  if (kind == BOPL_POSTERIOR_FP64) {
+    if (h->trsm_variant == 4) h->trsm_variant = 3;
+    h->use_ozaki = 0;
+  } else {
+    h->trsm_variant = 4;
+    h->use_ozaki = 1;
+    h->oz_digits = kind;
+  }
+  return BOPL_OK;
+}
+
+int bopl_get_posterior_kernel(const bopl_handle* h) {
+  if (!h) return -1;
+  return (h->trsm_variant == 4 && h->use_ozaki) ? h->oz_digits : BOPL_POSTERIOR_FP64;
+}
 
 int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
                    const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
@@ -267,7 +298,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     std::vector<signed char> oz_img;
     std::vector<double> oz_scale, oz_d64;
     if (h->use_ozaki) {
-      ozaki_prepare(Lp.data(), n_pad, oz_img, oz_scale);
+      ozaki_prepare(Lp.data(), n_pad, h->oz_digits, oz_img, oz_scale);
       const int nb64 = n_pad / 64;
       oz_d64.resize((size_t)nb64 * 64 * 64);
       for (int b = 0; b < nb64; ++b)
@@ -776,6 +807,14 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
       for (int b = 0; b < nblk; ++b) s += logdiag[(size_t)g * nblk + b];
       logdet_h[g] = 2.0 * s;
     }
+  bool oz_ok = false;
+  if (h->use_ozaki) {                 // int8 digit images + staging blocks of the INT8-tensor-pipe posterior kernel
+    if ((rc = ozaki_prepare_device(h, h->s_compute))) {
+      free_model(h);
+      return rc;
+    }
+    oz_ok = h->gp_host[0].OzL != nullptr;
+  }
   GpDev* gd;
   if ((rc = dev_upload(h, h->gp_host.data(), h->gp_host.size(), &gd))) {
     free_model(h);
@@ -784,6 +823,7 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   h->gp_dev = gd;
   h->has_winv = want_winv != 0;
   h->has_linv = want_linv != 0;
+  h->has_oz = oz_ok;
   h->has_model = true;
   h->F_valid = false;
   return BOPL_OK;

@@ -83,7 +83,8 @@ struct bopl_handle {
   void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
   int use_ozaki = 0;                   // BOPL_OZAKI=1: bopl_set_model also builds the int8 digit images (posterior_ozaki.cu)
   bool has_oz = false;
-  void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem = 0;
+  int oz_digits = 6;                   // digits of the model's images (fixed at upload): 6 = 47 fractional bits, 7 = 55
+  void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem[2] = {0, 0};
   size_t hsmall_cap = 0;
 };
 
@@ -139,7 +140,8 @@ int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, d
                             cudaStream_t st);
 bool trsm_t_fits(int d);
 bool ozaki_available(const bopl_handle* h);
-void ozaki_prepare(const double* Lp, int n_pad, std::vector<signed char>& img, std::vector<double>& scale);
+void ozaki_prepare(const double* Lp, int n_pad, int S, std::vector<signed char>& img, std::vector<double>& scale);
+int ozaki_prepare_device(bopl_handle* h, cudaStream_t st);
 void ozaki_pack_stage(const double* Dinv64, const double* Xs, const double* alpha, const double* scale, int n_pad, int d,
                       std::vector<double>& out);
 int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags, cudaStream_t st);

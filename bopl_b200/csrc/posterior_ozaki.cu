@@ -30,15 +30,18 @@ namespace bopl {
 namespace {
 
 constexpr int OB = 64;                       // rows per block row
-constexpr int OS = 6;                        // digits
 constexpr int OZ_MAXD = 12;                  // input dimensions the shared-memory plan is sized for
-constexpr int LIMG = OS * OB * OB;           // 24576 B: 384 stacked rows x 64 k, one off-diagonal block of L
-constexpr int LHALF = LIMG / 2;              // one k-step (32 k) of it
 constexpr int VPL = 128 * 32;                // 4096 B: one digit plane of V, 128 candidates x 32 k
-constexpr int VHALF = OS * VPL;              // 24576 B: the six planes of one k-step
-constexpr int VIMG = 2 * VHALF;              // 49152 B per solved block
-constexpr int OSTAGE = LHALF + VHALF;        // 36864 B per pipeline stage = one k-step of one (block row, block) pair
-constexpr int ONSTAGE = 4;
+// S = digits per operand: 6 (47 fractional bits; 21 digit pairs) or 7 (55 bits, i.e. every bit of an fp64 mantissa; 28 pairs)
+template <int S>
+struct Oz {
+  static constexpr int LIMG = S * OB * OB;          // S = 6: 24576 B: 384 stacked rows x 64 k, one off-diagonal block of L
+  static constexpr int LHALF = LIMG / 2;            // one k-step (32 k) of it
+  static constexpr int VHALF = S * VPL;             // the S planes of one k-step
+  static constexpr int VIMG = 2 * VHALF;            // per solved block
+  static constexpr int OSTAGE = LHALF + VHALF;      // per pipeline stage = one k-step of one (block row, block) pair (36864 / 43008 B)
+  static constexpr int ONSTAGE = S == 6 ? 4 : 3;
+};
 constexpr int NFRAG = 36;                    // lower-triangular 8x8 blocks of a 64x64 diagonal block
 constexpr int ONT = 320;                     // producer warp, MMA warp, eight compute warps
 constexpr int NCW = 8;
@@ -55,8 +58,9 @@ struct OzParams {
 
 // staged per block row: Dinv B fragments, scaled training rows transposed [q][64], alpha[64], row scales[64]
 __host__ __device__ inline int oz_sb_doubles(int d) { return NFRAG * 64 + (d + 2) * OB; }
+template <int S>
 __host__ __device__ inline size_t oz_smem_bytes(int d) {
-  return (size_t)ONSTAGE * OSTAGE + (size_t)2 * oz_sb_doubles(d) * 8 + (size_t)d * 128 * 8;
+  return (size_t)Oz<S>::ONSTAGE * Oz<S>::OSTAGE + (size_t)2 * oz_sb_doubles(d) * 8 + (size_t)d * 128 * 8;
 }
 
 __device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo, unsigned sbo) {
@@ -96,7 +100,10 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
                : "r"(taddr));
 }
 
+template <int OS>
 __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
+  constexpr int LIMG = Oz<OS>::LIMG, LHALF = Oz<OS>::LHALF, VHALF = Oz<OS>::VHALF, VIMG = Oz<OS>::VIMG, OSTAGE = Oz<OS>::OSTAGE,
+                ONSTAGE = Oz<OS>::ONSTAGE;
   extern __shared__ __align__(128) unsigned char osm[];
   const int d = p.d, n_pad = p.n_pad, nb = n_pad / OB;
   const int SBD = oz_sb_doubles(d);
@@ -185,7 +192,6 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     if (lane == 0) {
       unsigned gc = 0, uu = 0;            // k-steps consumed; accumulator generations started
       const unsigned lboA = 128 * 16, lboB = OS * OB * 16, sbo = 128;
-      const uint32_t id256 = idesc_s8(256), id192 = idesc_s8(192), id128 = idesc_s8(128), id64 = idesc_s8(64);
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         for (int i = 1; i < nb; ++i) {
           if (uu > 0) mbar_wait(&tmem_empty, (uu - 1) & 1);     // the previous block row's accumulators have been read
@@ -196,18 +202,17 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const unsigned lk = smem_u32(stage_s + (size_t)st * OSTAGE), vb = lk + LHALF;
             const uint32_t first = (ks2 == 0) ? 0u : 1u;
-            // V digit a (A operand, 128 candidates) x L digits 0..5-a (B operand rows 64 s ..) -> accumulators a..5 (64 columns each)
+            // V digit a (A operand, 128 candidates) x L digits 0..S-1-a (B operand rows 64 s ..) -> accumulators a..S-1 (64 columns
+            // each); an instruction covers at most 256 columns.  The a = 0 pair touches every accumulator: it clears them on the first k-step.
             const uint64_t bl = umma_desc(lk, lboB, sbo), bh = umma_desc(lk + 4 * 1024, lboB, sbo);
-            const uint64_t a0 = umma_desc(vb + 0 * VPL, lboA, sbo);
-            umma_i8(tmem + 0, a0, bl, id256, first);
-            umma_i8(tmem + 256, a0, bh, id128, first);
-            const uint64_t a1 = umma_desc(vb + 1 * VPL, lboA, sbo);
-            umma_i8(tmem + 64, a1, bl, id256, 1u);
-            umma_i8(tmem + 320, a1, bh, id64, 1u);
-            umma_i8(tmem + 128, umma_desc(vb + 2 * VPL, lboA, sbo), bl, id256, 1u);
-            umma_i8(tmem + 192, umma_desc(vb + 3 * VPL, lboA, sbo), bl, id192, 1u);
-            umma_i8(tmem + 256, umma_desc(vb + 4 * VPL, lboA, sbo), bl, id128, 1u);
-            umma_i8(tmem + 320, umma_desc(vb + 5 * VPL, lboA, sbo), bl, id64, 1u);
+#pragma unroll
+            for (int a = 0; a < OS; ++a) {
+              const uint64_t ad = umma_desc(vb + a * VPL, lboA, sbo);
+              const int ncols = 64 * (OS - a);
+              const uint32_t acc_flag = (a == 0) ? first : 1u;
+              umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols > 256 ? 256 : ncols), acc_flag);
+              if (ncols > 256) umma_i8(tmem + 64 * a + 256, ad, bh, idesc_s8(ncols - 256), acc_flag);
+            }
             umma_commit(&empty_bar[st]);
             ++gc;
           }
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
       const int kind = gp.kind;
       const double variance = gp.variance;
       const double vs = exp2(ceil(log2(sqrt(variance))) + 1.0);  // fixed-point scale of V: |V| <= sigma <= vs / 2
-      const double to_fix = 140737488355328.0 / vs;              // 2^47 / vs
+      const double to_fix = (OS == 6 ? 140737488355328.0 : 36028797018963968.0) / vs;   // 2^47 / vs (2^55 / vs)
       const double from_fix16 = vs * (1.0 / 1073741824.0);       // vs 2^-14 (digit product weight) 2^-16 (integer Horner)
       const double vmax = 0.5 * vs;
       __syncwarp();
@@ -310,13 +315,21 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             const double s0 = -(rs.x * from_fix16), s1 = -(rs.y * from_fix16);
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-              // weights 0..2 and 3..5 combined exactly in 64-bit integers (< 2^48), converted by the 1.5 * 2^52 trick (I2F.F64 runs
-              // at a quarter of the DFMA rate), joined by one FMA
+              // weights 0..2, 3..5 (3..4, 5..6 for seven digits) combined exactly in 64-bit integers (< 2^48), converted by the
+              // 1.5 * 2^52 trick (I2F.F64 runs at a quarter of the DFMA rate), joined by FMAs
               const long long hi3 = ((long long)a[0][x] << 16) + ((long long)a[1][x] << 8) + (long long)a[2][x];
-              const long long lo3 = ((long long)a[3][x] << 16) + ((long long)a[4][x] << 8) + (long long)a[5][x];
               const double dh = __longlong_as_double(0x4338000000000000LL + hi3) - 6755399441055744.0;
-              const double dl = __longlong_as_double(0x4338000000000000LL + lo3) - 6755399441055744.0;
-              const double h = fma(dl, 1.0 / 16777216.0, dh);
+              double h;
+              if constexpr (OS == 6) {
+                const long long lo3 = ((long long)a[3][x] << 16) + ((long long)a[4][x] << 8) + (long long)a[5][x];
+                const double dl = __longlong_as_double(0x4338000000000000LL + lo3) - 6755399441055744.0;
+                h = fma(dl, 1.0 / 16777216.0, dh);
+              } else {
+                const long long m2 = ((long long)a[3][x] << 8) + (long long)a[4][x], l2 = ((long long)a[5][x] << 8) + (long long)a[6][x];
+                const double dm = __longlong_as_double(0x4338000000000000LL + m2) - 6755399441055744.0;
+                const double dl = __longlong_as_double(0x4338000000000000LL + l2) - 6755399441055744.0;
+                h = fma(fma(dl, 1.0 / 65536.0, dm), 1.0 / 65536.0, dh);
+              }
               acc[x >> 1][nt][x & 1] = fma((x & 1) ? s1 : s0, h, acc[x >> 1][nt][x & 1]);
             }
           }
@@ -386,11 +399,15 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const double v = fmin(fmax(acc[mi][nt][e], -vmax), vmax);
-                const double z = fma(v, to_fix, 6755399441055744.0);          // 1.5 * 2^52 + round(v 2^47 / vs)
-                const unsigned long long u =
-                    (((unsigned long long)(unsigned)__double2hiint(z) << 32) | (unsigned)__double2loint(z)) + 0x0000808080808080ULL;
-                lo[nt][e] = (uint32_t)u;             // bytes 0..3: digits 5..2 (+128)
-                hi[nt][e] = (uint32_t)(u >> 32);     // bytes 0..1: digits 1..0 (+128)
+                unsigned long long u;
+                if constexpr (OS == 6) {
+                  const double z = fma(v, to_fix, 6755399441055744.0);          // 1.5 * 2^52 + round(v 2^47 / vs)
+                  u = (((unsigned long long)(unsigned)__double2hiint(z) << 32) | (unsigned)__double2loint(z)) + 0x0000808080808080ULL;
+                } else {
+                  u = (unsigned long long)__double2ll_rn(v * to_fix) + 0x0080808080808080ULL;   // 55 fractional bits: beyond the trick
+                }
+                lo[nt][e] = (uint32_t)u;             // bytes 0..3: digits S-1..S-4 (+128)
+                hi[nt][e] = (uint32_t)(u >> 32);     // bytes 0..S-5: digits S-5..0 (+128)
               }
             uint32_t plw[OS][4];
 #pragma unroll
@@ -398,12 +415,16 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
               const uint32_t p01 = __byte_perm(lo[2 * w][0], lo[2 * w][1], 0x5140), r01 = __byte_perm(lo[2 * w + 1][0], lo[2 * w + 1][1], 0x5140);
               const uint32_t p23 = __byte_perm(lo[2 * w][0], lo[2 * w][1], 0x7362), r23 = __byte_perm(lo[2 * w + 1][0], lo[2 * w + 1][1], 0x7362);
               const uint32_t ph = __byte_perm(hi[2 * w][0], hi[2 * w][1], 0x5140), rh = __byte_perm(hi[2 * w + 1][0], hi[2 * w + 1][1], 0x5140);
-              plw[5][w] = __byte_perm(p01, r01, 0x5410) ^ 0x80808080u;
-              plw[4][w] = __byte_perm(p01, r01, 0x7632) ^ 0x80808080u;
-              plw[3][w] = __byte_perm(p23, r23, 0x5410) ^ 0x80808080u;
-              plw[2][w] = __byte_perm(p23, r23, 0x7632) ^ 0x80808080u;
-              plw[1][w] = __byte_perm(ph, rh, 0x5410) ^ 0x80808080u;
-              plw[0][w] = __byte_perm(ph, rh, 0x7632) ^ 0x80808080u;
+              plw[OS - 1][w] = __byte_perm(p01, r01, 0x5410) ^ 0x80808080u;
+              plw[OS - 2][w] = __byte_perm(p01, r01, 0x7632) ^ 0x80808080u;
+              plw[OS - 3][w] = __byte_perm(p23, r23, 0x5410) ^ 0x80808080u;
+              plw[OS - 4][w] = __byte_perm(p23, r23, 0x7632) ^ 0x80808080u;
+              plw[OS - 5][w] = __byte_perm(ph, rh, 0x5410) ^ 0x80808080u;
+              plw[OS - 6][w] = __byte_perm(ph, rh, 0x7632) ^ 0x80808080u;
+              if constexpr (OS == 7) {
+                const uint32_t ph2 = __byte_perm(hi[2 * w][0], hi[2 * w][1], 0x7362), rh2 = __byte_perm(hi[2 * w + 1][0], hi[2 * w + 1][1], 0x7362);
+                plw[0][w] = __byte_perm(ph2, rh2, 0x5410) ^ 0x80808080u;
+              }
             }
 #pragma unroll
             for (int s = 0; s < OS; ++s) *reinterpret_cast<uint4*>(img + (size_t)s * VPL + (size_t)mi * 128) = make_uint4(plw[s][0], plw[s][1], plw[s][2], plw[s][3]);
@@ -450,12 +471,13 @@ bool ozaki_available(const bopl_handle* h) {
 
 int ozaki_stage_doubles(int d) { return oz_sb_doubles(d); }
 
-// Host side of the split: digit images of the off-diagonal blocks of the (front-padded, un-negated) factor Lp [n_pad x n_pad]
-// and the per-row power-of-two scales.  img: nb (nb-1)/2 blocks of LIMG bytes; column k of a block sits at position
+// Host side of the split: S-digit images of the off-diagonal blocks of the (front-padded, un-negated) factor Lp [n_pad x n_pad]
+// and the per-row power-of-two scales.  img: nb (nb-1)/2 blocks of S * 4096 bytes; column k of a block sits at position
 // 16 ((k % 8) / 2) + 2 (k / 8) + (k % 2) of its 64-deep k range (the order the compute warps publish V in).
-void ozaki_prepare(const double* Lp, int n_pad, std::vector<signed char>& img, std::vector<double>& scale) {
+void ozaki_prepare(const double* Lp, int n_pad, int S, std::vector<signed char>& img, std::vector<double>& scale) {
   const int nb = n_pad / OB;
-  img.assign((size_t)nb * (nb - 1) / 2 * LIMG, 0);
+  const size_t limg = (size_t)S * OB * OB;
+  img.assign((size_t)nb * (nb - 1) / 2 * limg, 0);
   scale.assign((size_t)n_pad, 1.0);
   for (int R = 0; R < n_pad; ++R) {
     const int i = R / OB;
@@ -464,23 +486,23 @@ void ozaki_prepare(const double* Lp, int n_pad, std::vector<signed char>& img, s
     if (mx > 0.0) {
       int e;
       std::frexp(mx, &e);                  // mx = f 2^e, 0.5 <= f < 1  ->  2^e > mx
-      scale[R] = std::ldexp(1.0, e + 1);   // >= 2 mx: digits of x / scale stay within +-2^46 / 2^47
+      scale[R] = std::ldexp(1.0, e + 1);   // >= 2 mx: digits of x / scale stay within +-2^(8S-2) / 2^(8S-1)
     }
   }
   for (int i = 1; i < nb; ++i)
     for (int kb = 0; kb < i; ++kb) {
-      signed char* base = img.data() + ((size_t)i * (i - 1) / 2 + kb) * LIMG;
+      signed char* base = img.data() + ((size_t)i * (i - 1) / 2 + kb) * limg;
       for (int r = 0; r < OB; ++r) {
         const int R = i * OB + r;
         const double inv = 1.0 / scale[R];
         for (int k = 0; k < OB; ++k) {
           const int kp = 16 * ((k % 8) / 2) + 2 * (k / 8) + (k % 2);
-          long long t = std::llrint(std::ldexp(Lp[(size_t)R * n_pad + kb * OB + k] * inv, 47));
-          for (int s = OS - 1; s >= 0; --s) {
+          long long t = std::llrint(std::ldexp(Lp[(size_t)R * n_pad + kb * OB + k] * inv, 8 * S - 1));
+          for (int s = S - 1; s >= 0; --s) {
             const int dg = (int)((t + 128) & 255) - 128;
             t = (t - dg) >> 8;
             const int rr = s * OB + r;
-            base[((size_t)(kp / 16) * (OS * OB / 8) + rr / 8) * 128 + (rr % 8) * 16 + (kp % 16)] = (signed char)dg;
+            base[((size_t)(kp / 16) * (S * OB / 8) + rr / 8) * 128 + (rr % 8) * 16 + (kp % 16)] = (signed char)dg;
           }
         }
       }
@@ -520,6 +542,161 @@ void ozaki_pack_stage(const double* Dinv64 /*[nb][64][64]*/, const double* Xs /*
   }
 }
 
+// ---------------------------------------------------------------------------------------------- device-side preparation
+// The same images and staging blocks from a model fitted on the device (bopl_fit_model): A holds the factor with its off-diagonal
+// 128-blocks negated and the diagonal 128-blocks as they are; the inverse of a 64 x 64 diagonal block is the matching diagonal
+// sub-block of the inverted 128 x 128 block.
+namespace {
+
+struct OzPrep {
+  const double* A;
+  const double* Dinv128;
+  const double* Xs;
+  const double* alpha;
+  signed char* img;
+  double* stage;
+};
+
+// power-of-two row scales (>= 2 max |L_Rk| over the columns left of the row's 64 x 64 diagonal block).  grid (n_pad / 8, G) x 256
+__global__ void oz_scale_kernel(const OzPrep* pp, int n_pad, int d) {
+  const OzPrep& q = pp[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, R = blockIdx.x * 8 + warp;
+  const int cols = OB * (R / OB);
+  double mx = 0.0;
+  for (int k = lane; k < cols; k += 32) mx = fmax(mx, fabs(q.A[(size_t)R * n_pad + k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    const int E = (__double2hiint(mx) >> 20) & 0x7ff;      // mx = 1.f 2^(E-1023) = 0.1f 2^(E-1022): frexp exponent E - 1022
+    const double sc = (mx > 0.0 && E > 0) ? __hiloint2double((E + 2) << 20, 0) : 1.0;   // 2^(E - 1022 + 1)
+    q.stage[(size_t)(R / OB) * oz_sb_doubles(d) + NFRAG * 64 + (d + 1) * OB + (R % OB)] = sc;
+  }
+}
+
+// digit image of off-diagonal block (i, kb), built in shared memory, written out with 16-byte stores.  grid (nb (nb-1) / 2, G) x 256
+template <int S>
+__global__ void oz_digits_kernel(const OzPrep* pp, int n_pad, int d) {
+  __shared__ __align__(16) signed char im[S * OB * OB];
+  const OzPrep& q = pp[blockIdx.y];
+  int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)blockIdx.x)) * 0.5);
+  while (i * (i - 1) / 2 > (int)blockIdx.x) --i;
+  while ((i + 1) * i / 2 <= (int)blockIdx.x) ++i;
+  const int kb = (int)blockIdx.x - i * (i - 1) / 2;
+  const int SBD = oz_sb_doubles(d);
+  for (int e = threadIdx.x; e < OB * OB; e += 256) {
+    const int r = e >> 6, k = e & 63, R = i * OB + r, C = kb * OB + k;
+    double v = q.A[(size_t)R * n_pad + C];
+    if ((R >> 7) != (C >> 7)) v = -v;
+    const double sc = q.stage[(size_t)i * SBD + NFRAG * 64 + (d + 1) * OB + r];
+    const long long t = __double2ll_rn(ldexp(v / sc, 8 * S - 1));
+    const unsigned long long u = ((unsigned long long)t + (S == 6 ? 0x0000808080808080ULL : 0x0080808080808080ULL)) ^
+                                 (S == 6 ? 0x0000808080808080ULL : 0x0080808080808080ULL);
+    const int kp = 16 * ((k & 7) >> 1) + 2 * (k >> 3) + (k & 1);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int rr = s * OB + r;
+      im[((kp >> 4) * (S * OB / 8) + (rr >> 3)) * 128 + (rr & 7) * 16 + (kp & 15)] = (signed char)(u >> (8 * (S - 1 - s)));
+    }
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(q.img + (size_t)blockIdx.x * (S * OB * OB));
+  for (int e = threadIdx.x; e < S * OB * OB / 16; e += 256) dst[e] = reinterpret_cast<const uint4*>(im)[e];
+}
+
+// staging block of block row b: Dinv fragments, scaled training rows transposed, alpha (the scales are already there).  grid (nb, G) x 256
+__global__ void oz_stage_kernel(const OzPrep* pp, int n_pad, int d) {
+  const OzPrep& q = pp[blockIdx.y];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  double* o = q.stage + (size_t)b * oz_sb_doubles(d);
+  const double* D = q.Dinv128 + (size_t)(b >> 1) * TRSM_BM * TRSM_BM + (size_t)(b & 1) * OB * (TRSM_BM + 1);   // sub-block (b&1, b&1)
+  const int g = lane >> 2, t = lane & 3;
+  int fi = 0;
+  for (int G = 1; G >= 0; --G)
+    for (int kt = 0; kt <= 4 * G + 3; ++kt)
+      for (int u = 0; u < 4; ++u) {
+        if (kt > 4 * G + u) continue;
+        if ((fi & 7) == grp) {
+          const int nt = 4 * G + u;
+          o[fi * 64 + 2 * lane + 0] = D[(size_t)(8 * nt + g) * TRSM_BM + 8 * kt + 2 * t];
+          o[fi * 64 + 2 * lane + 1] = D[(size_t)(8 * nt + g) * TRSM_BM + 8 * kt + 2 * t + 1];
+        }
+        ++fi;
+      }
+  double* xt = o + NFRAG * 64;
+  for (int e = threadIdx.x; e < OB * (d + 1); e += 256) {
+    const int r = e / (d + 1), c = e - r * (d + 1), R = b * OB + r;
+    xt[(size_t)c * OB + r] = c < d ? q.Xs[(size_t)R * d + c] : q.alpha[R];
+  }
+}
+
+}  // namespace
+
+// Builds OzL / OzStage of every GP in h->gp_host from its device-resident factor (call before the GpDev array is uploaded).
+int ozaki_prepare_device(bopl_handle* h, cudaStream_t st) {
+  const int G = (int)h->gp_host.size(), n_pad = h->n_pad, d = h->d, nb = n_pad / OB, S = h->oz_digits;
+  if (h->d > OZ_MAXD || n_pad > 16384 || nb < 1) return BOPL_OK;   // the kernel does not cover these shapes: fp64 kernel only
+  std::vector<OzPrep> prep(G);
+  const size_t img_bytes = std::max<size_t>(16, (size_t)nb * (nb - 1) / 2 * S * OB * OB), stage_bytes = (size_t)nb * oz_sb_doubles(d) * 8;
+  for (int gi = 0; gi < G; ++gi) {
+    void *pi = nullptr, *ps = nullptr;
+    BOPL_CUDA(h, cudaMalloc(&pi, img_bytes));
+    h->owned.push_back(pi);
+    BOPL_CUDA(h, cudaMalloc(&ps, stage_bytes));
+    h->owned.push_back(ps);
+    GpDev& gp = h->gp_host[gi];
+    prep[gi] = OzPrep{gp.Lneg, gp.Dinv, gp.Xs, gp.alpha, (signed char*)pi, (double*)ps};
+    gp.OzL = (const signed char*)pi;
+    gp.OzStage = (const double*)ps;
+  }
+  OzPrep* pd = nullptr;
+  BOPL_CUDA(h, cudaMalloc((void**)&pd, sizeof(OzPrep) * G));
+  h->owned.push_back(pd);
+  BOPL_CUDA(h, cudaMemcpyAsync(pd, prep.data(), sizeof(OzPrep) * G, cudaMemcpyHostToDevice, st));
+  oz_scale_kernel<<<dim3(n_pad / 8, G), 256, 0, st>>>(pd, n_pad, d);
+  BOPL_LAUNCH_CHECK(h, "oz_scale_kernel");
+  if (nb > 1) {
+    if (S == 7) oz_digits_kernel<7><<<dim3(nb * (nb - 1) / 2, G), 256, 0, st>>>(pd, n_pad, d);
+    else oz_digits_kernel<6><<<dim3(nb * (nb - 1) / 2, G), 256, 0, st>>>(pd, n_pad, d);
+    BOPL_LAUNCH_CHECK(h, "oz_digits_kernel");
+  }
+  oz_stage_kernel<<<dim3(nb, G), 256, 0, st>>>(pd, n_pad, d);
+  BOPL_LAUNCH_CHECK(h, "oz_stage_kernel");
+  BOPL_CUDA(h, cudaStreamSynchronize(st));     // prep (host vector) must outlive the copy
+  return BOPL_OK;
+}
+
+namespace {
+template <int S>
+int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
+  const long long items = (long long)p.ntiles * h->m;
+  const int grid = (int)std::min<long long>(items, h->sms);
+  const int nb = h->n_pad / OB;
+  int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)grid * nb * Oz<S>::VIMG);
+  if (rc) return rc;
+  p.scratch = (signed char*)h->oz_scratch;
+  {
+    // L2 budget as in posterior_trsm_t.cu: the digit image of the running attribute's factor stays resident; of the rest every CTA
+    // keeps the first blocks of its solved panel — the ones re-read most often
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
+    const double limg = (double)nb * (nb - 1) / 2 * Oz<S>::LIMG;
+    const double budget = (h->trsm_l2_keep_frac * (double)l2 - 1.5 * limg) / grid;
+    long long blocks = (long long)(budget / (double)Oz<S>::VIMG);
+    if (h->trsm_keep_blocks >= 0) blocks = h->trsm_keep_blocks;
+    p.keep_blocks = (int)std::max<long long>(0, std::min<long long>(blocks, nb));
+  }
+  const size_t smem = oz_smem_bytes<S>(h->d);
+  size_t& attr = h->oz_attr_smem[S - 6];
+  if (smem > attr) {
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  posterior_ozaki_kernel<S><<<grid, ONT, smem, st>>>(p);
+  BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
+  return BOPL_OK;
+}
+}  // namespace
+
 int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags, cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
   OzParams p;
@@ -536,31 +713,7 @@ int launch_posterior_ozaki(bopl_handle* h, const double* Xc, int N, int hsel, do
   p.pad = h->pad;
   p.ntiles = (N + 127) / 128;
   p.flags = flags;
-  const long long items = (long long)p.ntiles * h->m;
-  const int grid = (int)std::min<long long>(items, h->sms);
-  const int nb = h->n_pad / OB;
-  int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)grid * nb * VIMG);
-  if (rc) return rc;
-  p.scratch = (signed char*)h->oz_scratch;
-  {
-    // L2 budget as in posterior_trsm_t.cu: the digit image of the running attribute's factor stays resident; of the rest every CTA
-    // keeps the first blocks of its solved panel — the ones re-read most often
-    int l2 = 0;
-    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
-    const double limg = (double)nb * (nb - 1) / 2 * LIMG;
-    const double budget = (h->trsm_l2_keep_frac * (double)l2 - 1.5 * limg) / grid;
-    long long blocks = (long long)(budget / (double)VIMG);
-    if (h->trsm_keep_blocks >= 0) blocks = h->trsm_keep_blocks;
-    p.keep_blocks = (int)std::max<long long>(0, std::min<long long>(blocks, nb));
-  }
-  const size_t smem = oz_smem_bytes(h->d);
-  if (smem > h->oz_attr_smem) {
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->oz_attr_smem = smem;
-  }
-  posterior_ozaki_kernel<<<grid, ONT, smem, st>>>(p);
-  BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
-  return BOPL_OK;
+  return h->oz_digits == 7 ? launch_oz<7>(h, p, st) : launch_oz<6>(h, p, st);
 }
 
 }  // namespace bopl

@@ -49,7 +49,7 @@ def _torch():
 class Engine(object):
     """One GPU.  Methods taking `*_dev` arguments expect torch CUDA fp64 tensors on this engine's device."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, posterior_kernel=None):
         self.lib = _lib.load()
         torch = _torch()
         if not torch.cuda.is_available():
@@ -61,6 +61,8 @@ class Engine(object):
         self.h = h
         self.state = None
         self.sms = self.lib.bopl_device_sms(self.h)
+        if posterior_kernel is not None:
+            self.set_posterior_kernel(posterior_kernel)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
@@ -95,6 +97,16 @@ class Engine(object):
         return int(self.lib.bopl_launch_count(self.h))
 
     # ------------------------------------------------------------------ model
+    def set_posterior_kernel(self, kind):
+        """'fp64' (DMMA blocked solve, default), 'int8' (update on the int8 tensor pipe, 6-digit split) or 'int8x7' (7 digits).
+        Select before the model is uploaded / fitted: the digit images of the factor are built then (`bopl_set_posterior_kernel`)."""
+        self._check(self.lib.bopl_set_posterior_kernel(self.h, _lib.POSTERIOR_KERNELS[kind]))
+
+    @property
+    def posterior_kernel(self):
+        k = int(self.lib.bopl_get_posterior_kernel(self.h))
+        return {v: n for n, v in _lib.POSTERIOR_KERNELS.items()}[k]
+
     def set_model(self, state):
         if state.L is None:
             raise BoplError(-3, "this GPState was fitted on the device (Engine.fit_model) and holds no host factor to upload")

@@ -180,7 +180,7 @@ class MultiOutputGP(object):
     analytical_gradient_prediction = True
 
     def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
-                 fixed_hyps=False, device=0, gradients=True, fit_options=None, fit_on_device=True):
+                 fixed_hyps=False, device=0, gradients=True, fit_options=None, fit_on_device=True, posterior_kernel=None):
         self.output_dim = output_dim
         self.kernel = [None] * output_dim if kernel is None else kernel          # GPy kernel names ('Mat52', 'rbf', ...)
         self.noise_var = [None] * output_dim if noise_var is None else noise_var
@@ -192,7 +192,7 @@ class MultiOutputGP(object):
         self.gradients = gradients
         self.fit_options = dict(fit_options or {})        # n_burnin, subsample_interval, step_size, leapfrog_steps, max_iters
         self.fit_on_device = fit_on_device                # False: LAPACK on the host + upload (bopl_set_model), as round 1 did
-        self.engine = Engine(device)
+        self.engine = Engine(device, posterior_kernel)    # None: the library default (fp64, or $BOPL_POSTERIOR); 'int8' / 'int8x7'
         self._hyps = None
         self._h = 0
         self.state = None
@@ -201,14 +201,14 @@ class MultiOutputGP(object):
 
     # ---- construction helpers
     @classmethod
-    def from_state(cls, state, device=0):
-        self = cls(state.m, n_samples=state.H, device=device, gradients=state.Winv is not None)
+    def from_state(cls, state, device=0, posterior_kernel=None):
+        self = cls(state.m, n_samples=state.H, device=device, gradients=state.Winv is not None, posterior_kernel=posterior_kernel)
         self._load(state)
         return self
 
     @classmethod
-    def from_reference_model(cls, ref_model, device=0, gradients=True):
-        return cls.from_state(state_from_reference_model(ref_model, gradients), device)
+    def from_reference_model(cls, ref_model, device=0, gradients=True, posterior_kernel=None):
+        return cls.from_state(state_from_reference_model(ref_model, gradients), device, posterior_kernel)
 
     def set_hyperparameter_samples(self, variance, lengthscale, noise=None, kinds=None):
         """variance (m,H), lengthscale (m,H,d) or (m,H,1), noise (m,H) or None -> noise_var / 1e-6 (exact_feval)."""

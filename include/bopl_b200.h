@@ -59,6 +59,22 @@ const char* bopl_last_error(const bopl_handle* h);
 int bopl_device_sms(const bopl_handle* h);
 const char* bopl_build_info(void);
 
+/* Kernel behind bopl_posterior / bopl_uei* for batches above the small-batch limit (the reference has one NumPy path:
+ * GPy/inference/latent_function_inference/posterior.py:299-320 — dtrtrs on the cached factor, then the column square-sum).
+ *   BOPL_POSTERIOR_FP64   (default) fp64 DMMA.8x8x4 blocked triangular solve (posterior_trsm_t.cu);
+ *   BOPL_POSTERIOR_INT8   the same solve with its n^2/2 update on the int8 tensor pipe (tcgen05.mma kind::i8, TMEM): both operands
+ *                         split exactly into 6 base-256 digits (47 fractional bits against a power-of-two row scale), digit products
+ *                         accumulated exactly in s32, recombined in fp64 (posterior_ozaki.cu).  Variance within ~2e-11 sigma^2 of the
+ *                         fp64 kernel at n = 2000; 2.4x its speed.  Shapes it does not cover (d > 12, n > 16384) run the fp64 kernel.
+ *   BOPL_POSTERIOR_INT8_7 7 digits (55 bits: every bit of an fp64 mantissa), 28 instead of 21 digit products.
+ * Select BEFORE bopl_set_model / bopl_fit_model (the digit images of the factor are built at upload); switching back to FP64 is
+ * always allowed.  Environment default: BOPL_POSTERIOR=fp64|int8|int8x7. */
+#define BOPL_POSTERIOR_FP64 0
+#define BOPL_POSTERIOR_INT8 6
+#define BOPL_POSTERIOR_INT8_7 7
+int bopl_set_posterior_kernel(bopl_handle* h, int kind);
+int bopl_get_posterior_kernel(const bopl_handle* h);
+
 /* ---- model state ----------------------------------------------------------------------------------------
  * Replaces the cached state of m x H `GPy.models.GPRegression` instances that the reference keeps as live
  * Python objects: GPyOpt/models/gpmodel.py:123-140 (model_instances[h]) per attribute of

@@ -11,11 +11,11 @@ def oracle_model(p):
     return MultiOutputGPOracle(gps)
 
 
-def gpu_model(p, gradients=True, device=0):
+def gpu_model(p, gradients=True, device=0, posterior_kernel=None):
     from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
     state = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"],
                                        want_winv=gradients)
-    return MultiOutputGP.from_state(state, device=device)
+    return MultiOutputGP.from_state(state, device=device, posterior_kernel=posterior_kernel)
 
 
 def make_utility(p):

@@ -1,0 +1,192 @@
+"""GPU parity tests of the INT8-tensor-pipe posterior kernel (`posterior_kernel='int8'` / `'int8x7'`,
+bopl_b200/csrc/posterior_ozaki.cu): the same path as tests/test_gpu_parity.py — GPy posterior.py:299-320, gp.py:380-435 —
+with the n^2/2 update of the triangular solve carried out as exact int8 digit products on tcgen05 / TMEM.
+
+Tolerances.  The split keeps 47 (6 digits) or 55 (7 digits) fractional bits of every operand against a power-of-two scale
+(row maximum of L, prior standard deviation for V), so its error is ABSOLUTE in units of the prior variance:
+  * 7 digits: the same tolerance as the fp64 kernel (1e-9 relative + 64 x the oracle's own one-ulp-of-K* sensitivity);
+  * 6 digits: that, plus 1e-10 * prior variance (measured: 2e-11 at the benchmark shape n = 2000, 1e-12 at n = 300).
+Mean, acquisition values, argmax: as for the fp64 kernel (1e-9 of scale, identical argmax)."""
+import numpy as np
+import pytest
+
+from bopl_b200.synthetic import make_problem
+from oracle import acquisition as oacq
+from tests.helpers import gpu_acquisition, gpu_model, oracle_model, rel_err, scaled_err
+from tests.test_gpu_parity import CONFIGS, RTOL, check_close, variance_floor
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["int8", "int8x7"]
+ABS6 = 1e-10          # 6-digit split: absolute term, in units of the prior variance
+
+
+def check_var(v_g, v_o, om, p, X, kernel, what):
+    floor = variance_floor(om, X)
+    tol = RTOL * np.abs(v_o) + 64 * floor + 1e-300
+    if kernel == "int8":
+        tol = tol + ABS6 * p["variance"][:, om.h if hasattr(om, "h") else 0][:, None]
+    err = np.abs(v_g - v_o)
+    assert np.all(err <= tol), "%s (%s): worst err/tol %.3e, max err %.3e" % (what, kernel, np.max(err / tol), err.max())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", CONFIGS)
+def test_int8_posterior_named_configs(name, kernel):
+    p = make_problem(name, N=700)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
+    assert gm.engine.posterior_kernel == kernel
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    check_close(mu_g, mu_o, name + " mean")
+    check_var(v_g, v_o, om, p, p["Xc"], kernel, name + " var")
+    _, vn_o = om.predict_noiseless(p["Xc"])
+    _, vn_g = gm.predict_noiseless(p["Xc"])
+    check_var(vn_g, vn_o, om, p, p["Xc"], kernel, name + " noiseless var")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_int8_posterior_config_S_plain_relative(kernel):
+    """Benchmark shape (n=2000, m=3, d=10), first 4096 candidates: plain 1e-9 relative on mean AND variance, like the fp64 kernel;
+    the int8 kernels against the fp64 kernel itself: 1e-10 (6 digits) / 1e-12 (7 digits) relative."""
+    p = make_problem("S", N=4096)
+    om = oracle_model(p)
+    gm, g64 = gpu_model(p, gradients=False, posterior_kernel=kernel), gpu_model(p, gradients=False)
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    mu_d, v_d = g64.predict(p["Xc"])
+    assert rel_err(v_g, v_o) < RTOL, rel_err(v_g, v_o)
+    check_close(mu_g, mu_o, "S mean")
+    assert scaled_err(mu_g, mu_o) < 1e-11
+    assert rel_err(v_g, v_d) < (1e-10 if kernel == "int8" else 1e-12), rel_err(v_g, v_d)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n,N", [(1, 33), (5, 40), (63, 129), (64, 128), (65, 257), (127, 129), (129, 33), (300, 257), (513, 1000)])
+def test_int8_posterior_ragged_shapes(n, N, kernel):
+    """Training sets that are not multiples of the 64-row block (front padding), one block row only (no tensor work at all),
+    candidate counts that are not multiples of the 128-candidate tile."""
+    p = make_problem("portfolio1", n=n, N=N)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    check_close(mu_g, mu_o, "mean n=%d N=%d" % (n, N))
+    check_var(v_g, v_o, om, p, p["Xc"], kernel, "var n=%d N=%d" % (n, N))
+
+
+@pytest.mark.parametrize("kind", ["Mat52", "rbf", "Mat32", "ExpQuad"])
+def test_int8_posterior_kernel_kinds(kind):
+    p = make_problem("dtlz2a_quad", kind=kind, n=150, N=77)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel="int8")
+    mu_o, v_o = om.predict(p["Xc"])
+    mu_g, v_g = gm.predict(p["Xc"])
+    check_close(mu_g, mu_o, kind + " mean")
+    check_var(v_g, v_o, om, p, p["Xc"], "int8", kind + " var")
+
+
+def test_int8_posterior_hyper_samples_select():
+    p = make_problem("dtlz1a_linear", H=3, n=200, N=300)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel="int8")
+    for h in (2, 0, 1):
+        om.set_hyperparameters(h)
+        gm.set_hyperparameters(h)
+        mu_o, v_o = om.predict(p["Xc"])
+        mu_g, v_g = gm.predict(p["Xc"])
+        check_close(mu_g, mu_o, "mean h=%d" % h)
+        floor = variance_floor(om, p["Xc"])
+        assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + ABS6 * p["variance"][:, h][:, None])
+
+
+def test_int8_posterior_is_batch_and_permutation_invariant():
+    """Integer accumulation is exact and every other stage is per candidate: a candidate's numbers do not depend on its batch."""
+    p = make_problem("S", n=500, N=3000)
+    gm = gpu_model(p, gradients=False, posterior_kernel="int8")
+    mu, v = gm.predict(p["Xc"])
+    sl = slice(777, 777 + 1301)
+    mu_s, v_s = gm.predict(p["Xc"][sl])
+    assert np.array_equal(mu_s, mu[:, sl]) and np.array_equal(v_s, v[:, sl])
+    perm = np.random.RandomState(4).permutation(3000)
+    mu_p, v_p = gm.predict(p["Xc"][perm])
+    assert np.array_equal(mu_p, mu[:, perm]) and np.array_equal(v_p, v[:, perm])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_int8_posterior_of_a_model_fitted_on_the_device(kernel):
+    """bopl_fit_model builds the digit images on the device (oz_scale / oz_digits / oz_stage kernels): same numbers as the images
+    the host builds from an uploaded factor, up to the difference of the two Cholesky factorisations."""
+    from bopl_b200.models import MultiOutputGP
+    p = make_problem("S", n=700, N=900)
+    kinds, var, ell, noise = list(p["kinds"]), p["variance"], p["lengthscale"], p["noise"]
+    models = {}
+    for k in ("fp64", kernel):
+        gm = MultiOutputGP(p["m"], kernel=kinds, n_samples=1, device=0, gradients=False, posterior_kernel=k)
+        gm.set_hyperparameter_samples(var, ell, noise, kinds=kinds)
+        gm.updateModel(p["X"], list(p["Y"]))
+        models[k] = gm
+    mu_d, v_d = models["fp64"].predict(p["Xc"])
+    mu_g, v_g = models[kernel].predict(p["Xc"])
+    assert scaled_err(mu_g, mu_d) < 1e-12
+    assert rel_err(v_g, v_d) < (1e-10 if kernel == "int8" else 1e-12), rel_err(v_g, v_d)
+    om = oracle_model(p)
+    mu_o, v_o = om.predict(p["Xc"])
+    check_close(mu_g, mu_o, "device-fit mean")
+    assert rel_err(v_g, v_o) < RTOL
+
+
+def test_int8_uei_values_and_argmax():
+    """The whole acquisition through the int8 posterior kernel: 1e-9 of scale against the oracle, identical argmax and anchors as the
+    fp64 kernel's."""
+    p = make_problem("S", n=600, N=5000)
+    om = oracle_model(p)
+    gm, g64 = gpu_model(p, gradients=False, posterior_kernel="int8"), gpu_model(p, gradients=False)
+    a8 = gpu_acquisition(p, gm)._compute_acq(p["Xc"])[:, 0]
+    a64 = gpu_acquisition(p, g64)._compute_acq(p["Xc"])[:, 0]
+    marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], 1)
+    ref = oacq.aggregate(marg, p["use_full_support"], p["prob"])[:, 0]
+    check_close(a8, ref, "int8 uEI")
+    assert np.argmax(a8) == np.argmax(ref)
+    assert np.array_equal(np.argsort(-a8, kind="stable")[:20], np.argsort(-a64, kind="stable")[:20])
+
+
+def test_int8_kernel_selection_rules():
+    from bopl_b200._lib import BoplError
+    p = make_problem("portfolio1", n=80, N=50)
+    gm = gpu_model(p)                                   # fp64 model: no digit images
+    with pytest.raises(BoplError):
+        gm.engine.set_posterior_kernel("int8")
+    g8 = gpu_model(p, posterior_kernel="int8")
+    with pytest.raises(BoplError):
+        g8.engine.set_posterior_kernel("int8x7")        # images of the other width
+    mu8, v8 = g8.predict(p["Xc"])
+    g8.engine.set_posterior_kernel("fp64")              # always allowed: the fp64 operands are always there
+    mu64, v64 = g8.predict(p["Xc"])
+    mu_r, v_r = gm.predict(p["Xc"])
+    assert np.array_equal(mu64, mu_r) and np.array_equal(v64, v_r)
+    assert scaled_err(v8, v64) < 1e-9
+    # shapes the int8 kernel does not cover (d > 12) run the fp64 kernel — same library, same device, not a CPU fallback: bit-identical
+    from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
+    rs = np.random.RandomState(5)
+    d, m, n = 14, 2, 90
+    X, Xc = rs.uniform(size=(n, d)), rs.uniform(size=(70, d))
+    Y = np.stack([np.sin(X @ rs.normal(size=d)) for _ in range(m)])
+    st = state_from_hyperparameters(X, Y, ["Mat52"] * m, np.ones((m, 1)), np.full((m, 1, d), 3.0), np.full((m, 1), 1e-4))
+    a, b = MultiOutputGP.from_state(st, posterior_kernel="int8"), MultiOutputGP.from_state(st)
+    assert np.array_equal(a.predict(Xc)[1], b.predict(Xc)[1])
+
+
+def test_int8_full_size_config_S():
+    """Config S at BASELINE.json's full size through the reference-facing call with the int8 kernel: finite non-negative scores,
+    anchors = stable argsort, bitwise sub-batch reproducibility, and the same top-20 anchors as the fp64 kernel."""
+    p = make_problem("S")
+    gm = gpu_model(p, gradients=False, posterior_kernel="int8")
+    acq = gpu_acquisition(p, gm)
+    val, idx, a = acq.top_candidates(p["Xc"], 20, want_acq=True)
+    assert a.shape == (2 ** 20,) and np.all(np.isfinite(a)) and np.all(a >= 0.0)
+    want = np.argsort(-a, kind="stable")[:20]
+    assert np.array_equal(idx, want) and np.array_equal(val, a[want])
+    sl = slice(300000, 300000 + 70001)
+    assert np.array_equal(acq._compute_acq(p["Xc"][sl])[:, 0], a[sl])
+    g64 = gpu_model(p, gradients=False)
+    val64, idx64, a64 = gpu_acquisition(p, g64).top_candidates(p["Xc"], 20, want_acq=True)
+    assert np.array_equal(idx, idx64)
+    assert scaled_err(a, a64) < 1e-10
