@@ -143,7 +143,7 @@ def run_gpu(args):
     d, m = p["d"], p["m"]
     state = state_from_hyperparameters(p["X"], p["Y"], p["kinds"], p["variance"], p["lengthscale"], p["noise"], want_winv=False,
                                        want_linv=False)
-    model = MultiOutputGP.from_state(state, device=local_rank)
+    model = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel=args.posterior)
     eng = model.engine
     theta = p["theta"]
     udist = UtilityDistribution(support=theta, prob_dist=np.ones(len(theta)) / len(theta), use_full_support=False,
@@ -189,6 +189,23 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the fp64 DMMA kernel on the same inputs, outside the timed region: its launch time and the largest relative difference of the
+    # int8 kernel's variance from it over a whole wave of candidates (rank 0 of a 1-GPU run only)
+    fp64_ms, parity_rel = None, None
+    if args.posterior != "fp64" and world == 1 and not args.no_fp64_leg:
+        m64 = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel="fp64")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        m64.engine.posterior_dev(Xd, 0)
+        ev[0].record()
+        mean64, var64 = m64.engine.posterior_dev(Xd, 0)
+        ev[1].record()
+        torch.cuda.synchronize()
+        fp64_ms = float(ev[0].elapsed_time(ev[1]))
+        mean8, var8 = eng.posterior_dev(Xd, 0)
+        parity_rel = float(((var8 - var64).abs() / var64.abs()).max().item())
+        del m64, mean64, var64, mean8, var8
+        torch.cuda.empty_cache()
+
     for _ in range(args.warmup):
         step(False)
     barrier()
@@ -232,17 +249,47 @@ def run_gpu(args):
         peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
         peak_tf = float(peaks["fp64_dgemm_tflops"])
         flops_launch = algorithmic_flops_per_candidate(m, w["n"], d) * float(N)
-        achieved = flops_launch / (trsm_ms_avg * 1e-3) * 1e-12
+        fp64_equiv = flops_launch / (trsm_ms_avg * 1e-3) * 1e-12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "trsm_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch_int8" if args.posterior != "fp64" else "dram_bytes_per_launch")
+        if args.posterior == "fp64":
+            roof = {"bound": "tensor", "kernel": "posterior_trsm_t_kernel (fused K*, FP64 DMMA blocked triangular solve, mean, variance)",
+                    "achieved": fp64_equiv, "peak": peak_tf, "unit": "TFLOP/s", "frac": fp64_equiv / peak_tf,
+                    "traffic": traffic, "kernel_ms": trsm_ms_avg, "flops_per_launch": flops_launch,
+                    "peak_source": "profiles/r01_fp64_peaks.json: cuBLAS DGEMM 8192^3 measured on this pool's B200 "
+                                   "(MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.0)"}
+        else:
+            # the triangular-solve update runs as exact int8 digit products on tcgen05: S (S + 1) / 2 products per fp64 multiply-add
+            S = 6 if args.posterior == "int8" else 7
+            pairs = S * (S + 1) // 2
+            int8_ops = 2.0 * pairs * m * float(N) * w["n"] * w["n"] / 2.0
+            i8 = json.load(open(os.path.join(ROOT, "profiles", "r01_int8_peaks.json")))
+            peak_i8 = float(i8["int8_tops_N256"])
+            ach = int8_ops / (trsm_ms_avg * 1e-3) * 1e-12
+            roof = {"bound": "tensor",
+                    "kernel": "posterior_ozaki_kernel<%d> (fused K*, blocked triangular solve with the n^2/2 update as %d exact int8 digit "
+                              "products per fp64 multiply-add on tcgen05.mma kind::i8 / TMEM, fp64 diagonal solve on DMMA, mean, variance)" % (S, pairs),
+                    "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8,
+                    "unit_note": "int8 tensor tera-ops/s (2 per multiply-add); algorithmic ops = 2 * %d * m * N * n^2/2" % pairs,
+                    "traffic": traffic, "kernel_ms": trsm_ms_avg, "int8_ops_per_launch": int8_ops, "flops_per_launch": flops_launch,
+                    "fp64_equivalent": {"achieved": fp64_equiv, "peak": peak_tf, "unit": "TFLOP/s", "frac": fp64_equiv / peak_tf,
+                                        "note": "the same algorithmic fp64 flops against the cuBLAS DGEMM peak the fp64 kernel is bound by"},
+                    "peak_source": "profiles/r01_int8_peaks.json: back-to-back tcgen05.mma kind::i8 M=128 N=256 K=32 on all SMs "
+                                   "(tools/int8_umma_probe.cu); the FP64 pipe time-shares with it (profiles/r01_fp64_vs_int8.json)"}
+            if fp64_ms is not None:
+                roof["fp64_kernel"] = {"kernel": "posterior_trsm_t_kernel", "kernel_ms": fp64_ms,
+                                       "frac_of_dgemm_peak": flops_launch / (fp64_ms * 1e-3) * 1e-12 / peak_tf,
+                                       "int8_vs_fp64_max_rel_var": parity_rel}
         out = {
             "metric": METRIC, "value": evals_per_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "S: d=10 m=3 n=%d N=%d candidates per GPU, n_w=%d L=%d H=1 Matern52-ARD noise=1e-6 %s utility, top-%d anchors"
                                    % (w["n"], N, w["n_w"], w["L"], args.utility, K_ANCHOR),
+                       "posterior_kernel": args.posterior,
                        "sharding": "candidates row-sharded, %d per rank; all-gather of top-%d records only" % (N, K_ANCHOR),
                        "l2": "working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2, and a 256 MB flush write between steps"},
             "clocks": sampler.summary(),
@@ -251,11 +298,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(N * 8 + K_ANCHOR * 16), "steps": e2e_steps,
                     "api": "uEI.top_candidates -> bopl_uei_host (pinned host candidates -> scores + top-20 on the host)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "posterior_trsm_t_kernel (fused K*, FP64 DMMA blocked triangular solve, mean, variance)",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": traffic, "kernel_ms": trsm_ms_avg, "flops_per_launch": flops_launch,
-                         "peak_source": "profiles/r01_fp64_peaks.json: cuBLAS DGEMM 8192^3 measured on this pool's B200 "
-                                        "(MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.0)"},
+            "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
             pc = make_problem("S", n=w["n"], N=args.cpu_sample, n_w=w["n_w"], L=w["L"], utility=args.utility)
@@ -285,6 +328,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--posterior", default="int8", choices=["int8", "int8x7", "fp64"],
+                    help="posterior kernel: int8 = 6-digit split on the int8 tensor pipe (default), int8x7 = 7 digits, fp64 = DMMA kernel")
+    ap.add_argument("--no-fp64-leg", action="store_true", help="skip the fp64-kernel comparison launch before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
