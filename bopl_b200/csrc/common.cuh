@@ -180,45 +180,59 @@ int launch_topk(bopl_handle* h, const double* acq, int N, int k, long long index
 // K* generation was latency-bound because of it (profiles/r01_trsm_v1_ncu.md).  Both are accurate to ~1 ulp over the
 // ranges the kernels produce (checked against the oracle at 1e-13 in tests/test_gpu_parity.py::test_cross_cov_kernels).
 
-// sqrt(a) for a >= 0 (0 and denormals -> 0): MUFU.RSQ64H seed (2^-22.9), two Newton steps on 1/sqrt, one on sqrt.
+// sqrt(a) for a >= 0 (0 and denormals -> 0): MUFU.RSQ64H seed (2^-22.9), ONE Newton step on 1/sqrt (2^-45), then the residual
+// step on sqrt itself, which squares the error again (tools/kern_math_check.cu: <= 0.5 ulp + rounding over 1e-300 .. 1e300).
 __device__ __forceinline__ double sqrt_nonneg(double a) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
   const double h = 0.5 * a;
-  double e = fma(-h, y * y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h, y * y, 0.5);
+  const double e = fma(-h, y * y, 0.5);
   y = fma(y, e, y);
   double r = a * y;
   r = fma(fma(-r, r, a), 0.5 * y, r);
   return (a >= 1e-300) ? r : 0.0;
 }
 
+// 2^(j/64), j = 0..63, correctly rounded.
+__device__ const double EXP2_64TH[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
 // exp(x) for x <= 0 (clamped at -700: the result is then ~1e-304 instead of a denormal or 0).
-// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2; degree-13 Taylor polynomial (remainder 4e-18); exponent insertion.
+// x = (64 e + j) ln2/64 + r, |r| <= ln2/128 (Cody-Waite, two-part ln2/64): exp(x) = 2^e T_j (1 + expm1(r)) with T_j = 2^(j/64) from a
+// 512-byte table and expm1(r) = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120) (remainder 3.5e-17) — 6 fp64 operations after the reduction
+// instead of the 13-term polynomial the |r| <= ln2/2 reduction needs: K* generation competes with the tensor work for the FP64
+// pipe (profiles/r01_fp64_vs_int8.json), the table read and the index arithmetic do not.  T_j (1 + em) is formed as fma(T_j, em, T_j):
+// only the table entry's and the final rounding remain (tools/kern_math_check.cu: <= 1.0 ulp).
 __device__ __forceinline__ double exp_nonpos(double x) {
   x = fmax(x, -700.0);
   const double magic = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest integer in the low word
-  double kd = fma(x, 1.4426950408889634074, magic);
-  const int k = __double2loint(kd);
+  double kd = fma(x, 0x1.71547652b82fep+6, magic);
+  const int n = __double2loint(kd);
   kd -= magic;
-  double r = fma(kd, -0x1.62e42fee00000p-1, x);
-  r = fma(kd, -0x1.a39ef35793c76p-33, r);
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, r, 1.0 / 479001600.0);
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  double r = fma(kd, -0x1.62e42fee00000p-7, x);
+  r = fma(kd, -0x1.a39ef35793c76p-39, r);
+  const double t = __ldg(&EXP2_64TH[n & 63]);
+  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  const double em = fma(q, r * r, r);
+  const double p = fma(t, em, t);
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
 }
 
 // Stationary kernels as functions of the squared scaled distance r2 (already clipped at 0).
@@ -239,7 +253,7 @@ __device__ __forceinline__ double kern_value(int kind, double variance, double r
 }
 
 // Eight kernel values at once, written operation-by-operation across the eight lanes so that the eight independent
-// sqrt / exp dependency chains interleave in the instruction stream (the same arithmetic as kern_value).
+// sqrt / exp dependency chains interleave in the instruction stream (the same arithmetic as kern_value, bit for bit).
 __device__ __forceinline__ void kern_value8(int kind, double variance, const double* r2, double* out) {
   double r[8], x[8], pre[8];
 #pragma unroll
@@ -249,15 +263,9 @@ __device__ __forceinline__ void kern_value8(int kind, double variance, const dou
     r[u] = y;
   }
   {
-    double h[8], e[8];
+    double e[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) h[u] = 0.5 * r2[u];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) e[u] = fma(-h[u], r[u] * r[u], 0.5);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) r[u] = fma(r[u], e[u], r[u]);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) e[u] = fma(-h[u], r[u] * r[u], 0.5);
+    for (int u = 0; u < 8; ++u) e[u] = fma(-(0.5 * r2[u]), r[u] * r[u], 0.5);
 #pragma unroll
     for (int u = 0; u < 8; ++u) r[u] = fma(r[u], e[u], r[u]);      // 1/sqrt
 #pragma unroll
@@ -288,31 +296,33 @@ __device__ __forceinline__ void kern_value8(int kind, double variance, const dou
       x[u] = -0.5 * (r[u] * r[u]);
     }
   }
-  int k[8];
+  int n[8];
+  double t[8], q[8];
   const double magic = 6755399441055744.0;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     x[u] = fmax(x[u], -700.0);
-    double kd = fma(x[u], 1.4426950408889634074, magic);
-    k[u] = __double2loint(kd);
+    double kd = fma(x[u], 0x1.71547652b82fep+6, magic);
+    n[u] = __double2loint(kd);
     kd -= magic;
-    double rr = fma(kd, -0x1.62e42fee00000p-1, x[u]);
-    x[u] = fma(kd, -0x1.a39ef35793c76p-33, rr);
+    const double rr = fma(kd, -0x1.62e42fee00000p-7, x[u]);
+    x[u] = fma(kd, -0x1.a39ef35793c76p-39, rr);
   }
-  double pl[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) pl[u] = fma(1.0 / 6227020800.0, x[u], 1.0 / 479001600.0);
-  const double c[11] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
-                        1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+  for (int u = 0; u < 8; ++u) t[u] = __ldg(&EXP2_64TH[n[u] & 63]);
 #pragma unroll
-  for (int s = 0; s < 11; ++s)
+  for (int u = 0; u < 8; ++u) q[u] = fma(x[u], 1.0 / 120.0, 1.0 / 24.0);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) pl[u] = fma(pl[u], x[u], c[s]);
+  for (int u = 0; u < 8; ++u) q[u] = fma(q[u], x[u], 1.0 / 6.0);
 #pragma unroll
-  for (int u = 0; u < 8; ++u) pl[u] = fma(pl[u], x[u], 1.0);
+  for (int u = 0; u < 8; ++u) q[u] = fma(q[u], x[u], 0.5);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) q[u] = fma(q[u], x[u] * x[u], x[u]);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) q[u] = fma(t[u], q[u], t[u]);
 #pragma unroll
   for (int u = 0; u < 8; ++u)
-    out[u] = pre[u] * __hiloint2double(__double2hiint(pl[u]) + (k[u] << 20), __double2loint(pl[u]));
+    out[u] = pre[u] * __hiloint2double(__double2hiint(q[u]) + ((n[u] >> 6) << 20), __double2loint(q[u]));
 }
 
 // value and g = (dK/dr)/r with 1/r := 0 at r == 0  (stationary.py:227-234 _inv_dist; dK_dr :532-533, :443-444, :597-598; rbf.py:45-46)
