@@ -1,28 +1,32 @@
 // posterior_ozaki.cu — kernels (1)+(2) of the hot path with the many-right-hand-side update on the INT8 tensor pipe
-// (tcgen05.mma kind::i8, TMEM accumulators) by an error-free split ("Ozaki scheme") of the fp64 operands.  OPT-IN
-// (BOPL_TRSM_VARIANT=4 + a model uploaded with bopl_set_model while BOPL_OZAKI=1); the DMMA kernel stays the default.
+// (tcgen05.mma kind::i8, TMEM accumulators) by an error-free split ("Ozaki scheme") of the fp64 operands.  Selected with
+// bopl_set_posterior_kernel(h, BOPL_POSTERIOR_INT8 | BOPL_POSTERIOR_INT8_7) (or BOPL_POSTERIOR=int8|int8x7) before the model is
+// uploaded or fitted; the fp64 DMMA kernel (posterior_trsm_t.cu) stays the library default.  DESIGN.md §3.1b.
 //
 // Same mathematics as posterior_trsm_t.cu (posterior.py:299-320, gp.py:380-435, linalg.py:92-111): left-looking blocked forward
 // substitution V_i = Dinv_i (K*_i - sum_{k<i} L_ik V_k), 64-row blocks, tile = 128 candidates, then mean / variance.
 // What changes is the update sum_k L_ik V_k (n^2/2 FMAs per candidate, 97 % of the work).  sm_100a has no fp64 tcgen05 kind,
 // but its int8 kind is 128x faster than the fp64 pipe, and an fp64 product can be split into exact int8 products:
-//   * every row of the off-diagonal part of L is scaled by a power of two ls_r >= 2 max|L_rk| and written in S = 6 balanced
-//     base-256 digits (int8): L_rk = ls_r * sum_s d_s 2^(-7-8s)  (47 fractional bits, done once on the host);
+//   * every row of the off-diagonal part of L is scaled by a power of two ls_r >= 2 max|L_rk| and written in S = 6 (or 7) balanced
+//     base-256 digits (int8): L_rk = ls_r * sum_s d_s 2^(-7-8s)  (47 / 55 fractional bits; once per model, host or device);
 //   * |V| <= sqrt(variance) (because var = variance - |V|^2 >= 0), so V is written in fixed point against vs = 2^ceil(log2 sigma)+1
 //     the same way, on the fly, by the warp that solved it;
-//   * digit products are accumulated EXACTLY in s32 by the tensor core, one accumulator per digit weight g = s_L + s_V < 6
-//     (|acc| <= 6 * n * 2^14 < 2^31 for n <= 16384), and combined once per block row in fp64 (Horner in 2^-8).
-// Dropped terms (g >= 6) are below 2^-48 of ls_r * vs * n: measured 5e-12 relative on the variance at the benchmark shape, vs
-// 3e-14 for the fp64 kernel (tests/test_gpu_parity.py::test_ozaki_*).
+//   * digit products are accumulated EXACTLY in s32 by the tensor core, one accumulator per digit weight g = s_L + s_V < S
+//     (|acc| <= S * n * 2^14 < 2^31 for n <= 16384), and combined once per block row in fp64.
+// Dropped terms (g >= S) are below 2^(-8S) of ls_r * vs * n: measured against the fp64 kernel on 2^20 candidates of the benchmark
+// shape, 3.4e-11 relative on the variance with 6 digits and 2.9e-13 with 7 (tests/test_gpu_int8_posterior.py).
 //
-// One instruction covers several digit pairs: the six digit planes of an L chunk are stacked as ONE 384-row B operand, so
-// V digit a against L digits 0..5-a is a single N = 64 (6 - a) MMA (split at N = 256) whose output columns are exactly the
-// accumulators g = a..5 — 8 instructions per 32-deep k-step instead of 21.
+// One instruction covers several digit pairs: the S digit planes of an L block are stacked as ONE 64 S-row B operand, so
+// V digit a against L digits 0..S-1-a is a single N = 64 (S - a) MMA (split at N = 256) whose output columns are exactly the
+// accumulators g = a..S-1 — 8 (10) instructions per 32-deep k-step instead of 21 (28).
 //
-// Roles (192 threads, one persistent CTA per SM): warp 0 lane 0 streams operand chunks with cp.async.bulk (L digit images from
-// the model, V digit images from this CTA's scratch panel) through a 2-stage ring; warp 1 lane 0 issues the MMAs; warps 2-5
-// (thread = candidate = TMEM lane) generate K*, read the accumulators, apply the inverted 64x64 diagonal block, accumulate
-// mean and sum V^2, and publish the digits of the solved block.
+// Roles (320 threads, one persistent CTA per SM): warp 0 lane 0 streams operand k-steps with cp.async.bulk (L digit images from
+// the model, V digit images from this CTA's scratch panel) through a 4-stage (3 for S = 7) ring plus one staging block per block row;
+// warp 1 lane 0 issues the MMAs; warps 2-9 each own 16 candidates x the 64 rows of the block row in the DMMA C-fragment layout
+// (tcgen05.ld.16x256b delivers the accumulators in exactly that layout): K* into the fragments, accumulators recombined and
+// subtracted, inverted diagonal block applied in place on DMMA, mean and sum V^2, digits of the solved block published.
+// The FP64 pipe and the int8 tensor pipe time-share on this part (tools/fp64_vs_umma_probe.cu), so the launch costs about
+// (tensor time) + (fp64 time); profiles/r01_summary.md §A has the measurements.
 #include "pipeline.cuh"
 
 namespace bopl {
