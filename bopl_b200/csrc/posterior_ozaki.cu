@@ -58,6 +58,7 @@ struct OzParams {
   signed char* scratch;   // [grid][n_pad/64][VIMG]
   int H, hsel, m, N, d, n_pad, pad, ntiles, flags;
   int keep_blocks;        // solved blocks below this index are kept in L2 (evict_last), the rest is streamed
+  long long* trace;       // TRACE instantiation only
 };
 
 // staged per block row: Dinv B fragments, scaled training rows transposed [q][64], alpha[64], row scales[64]
@@ -104,7 +105,10 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
                : "r"(taddr));
 }
 
-template <int OS>
+// TRACE: CTA 0 records clock64 at its phase boundaries into p.trace (tools/ozaki_trace.py; BOPL_OZ_TRACE=1), slot layout
+// [row][8]: 0 K* start, 1 K* done, 2 accumulators full, 3 recombined (TMEM released), 4 diagonal solve done, 5 digits published
+// (compute warp 2, lane 0); 6 first MMA of the row issued, 7 last MMA of the row committed (MMA thread).  First work item only.
+template <int OS, bool TRACE>
 __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   constexpr int LIMG = Oz<OS>::LIMG, LHALF = Oz<OS>::LHALF, VHALF = Oz<OS>::VHALF, VIMG = Oz<OS>::VIMG, OSTAGE = Oz<OS>::OSTAGE,
                 ONSTAGE = Oz<OS>::ONSTAGE;
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         for (int i = 1; i < nb; ++i) {
           if (uu > 0) mbar_wait(&tmem_empty, (uu - 1) & 1);     // the previous block row's accumulators have been read
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 8 + 6] = clock64();
           for (int ks2 = 0; ks2 < 2 * i; ++ks2) {
             const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
             mbar_wait(&full_bar[st], use & 1);
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             ++gc;
           }
           umma_commit(&acc_full);
+          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 8 + 7] = clock64();
           ++uu;
         }
       }
@@ -259,6 +265,8 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         const double* alpha_s = xt_s + d * OB;
         const double* scale_s = alpha_s + OB;
 
+        const bool tr = TRACE && blockIdx.x == 0 && item == 0 && warp == 2 && lane == 0;
+        if (tr) p.trace[i * 8 + 0] = clock64();
         // ---- K*^T of the block row straight into the fragments (rows in the front padding are masked), mean
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -305,8 +313,10 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         }
 
         // ---- subtract sum_k L_ik V_k: six s32 accumulators per (candidate, row), Horner in 2^-8, then the two power-of-two scales
+        if (tr) p.trace[i * 8 + 1] = clock64();
         if (i > 0) {
           mbar_wait(&acc_full, uu & 1);
+          if (tr) p.trace[i * 8 + 2] = clock64();
           ++uu;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty);
         }
+        if (tr) p.trace[i * 8 + 3] = clock64();
 
         // ---- diagonal block, in registers and in place: V^T[:, nt] = sum_{kt <= nt} rhs^T[:, kt] * Dinv^T[kt, nt]
         {
@@ -389,6 +400,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb_empty[buf]);
+        if (tr) p.trace[i * 8 + 4] = clock64();
         ++sbc;
 
         // ---- publish the digits of V_i for the later block rows.  Position of row 8 nt + 2 t + e inside the 64-deep block:
@@ -438,6 +450,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           asm volatile("fence.proxy.async;\n" ::: "memory");
         }
         mbar_arrive(&v_pub);
+        if (tr) p.trace[i * 8 + 5] = clock64();
       }
       // ---- finalize the item: the four t-lanes of a candidate hold its partial sums
 #pragma unroll
@@ -692,10 +705,32 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
   const size_t smem = oz_smem_bytes<S>(h->d);
   size_t& attr = h->oz_attr_smem[S - 6];
   if (smem > attr) {
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  posterior_ozaki_kernel<S><<<grid, ONT, smem, st>>>(p);
+  p.trace = nullptr;
+  if (const char* tf = getenv("BOPL_OZ_TRACE")) {      // diagnostic: phase timestamps of CTA 0's first work item -> text file
+    long long* tb = nullptr;
+    const size_t tbytes = (size_t)nb * 8 * sizeof(long long);
+    BOPL_CUDA(h, cudaMalloc((void**)&tb, tbytes));
+    BOPL_CUDA(h, cudaMemsetAsync(tb, 0, tbytes, st));
+    p.trace = tb;
+    posterior_ozaki_kernel<S, true><<<grid, ONT, smem, st>>>(p);
+    BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
+    std::vector<long long> host((size_t)nb * 8);
+    BOPL_CUDA(h, cudaStreamSynchronize(st));
+    BOPL_CUDA(h, cudaMemcpy(host.data(), tb, tbytes, cudaMemcpyDeviceToHost));
+    cudaFree(tb);
+    if (FILE* f = fopen(tf, "w")) {
+      for (int i = 0; i < nb; ++i) {
+        for (int c = 0; c < 8; ++c) fprintf(f, "%lld%c", host[(size_t)i * 8 + c], c == 7 ? '\n' : ' ');
+      }
+      fclose(f);
+    }
+    return BOPL_OK;
+  }
+  posterior_ozaki_kernel<S, false><<<grid, ONT, smem, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
   return BOPL_OK;
 }
