@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
 SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu", "posterior_ozaki.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = (["-DOZ_SWAP_ROLES"] if os.environ.get("OZ_SWAP_ROLES") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0"]
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}

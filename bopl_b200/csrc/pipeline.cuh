@@ -69,6 +69,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
+// Same wait for single-thread roles that sit next to working warps on their SM sub-partition (bulk-copy producer, MMA issuer):
+// sleeps between polls so that the spin does not compete with them for issue slots.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity, unsigned ns) {
+  unsigned done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
+
 // Copy a ROWS x KW tile of doubles (row stride `ld` doubles in global) into shared memory as [row][KW].
 // KW == 16: 16-byte chunks XOR-swizzled with (row & 1) << 2 (conflict-free LDS.128 fragments); KW == 8: plain.
 template <int ROWS, int KW, int NT>

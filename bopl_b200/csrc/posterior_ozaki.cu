@@ -49,6 +49,11 @@ struct Oz {
 constexpr int NFRAG = 36;                    // lower-triangular 8x8 blocks of a 64x64 diagonal block
 constexpr int ONT = 320;                     // producer warp, MMA warp, eight compute warps
 constexpr int NCW = 8;
+#ifndef OZ_SWAP_ROLES
+constexpr int PROD_WARP = 0, MMA_WARP = 1;
+#else
+constexpr int PROD_WARP = 1, MMA_WARP = 0;
+#endif
 
 struct OzParams {
   const GpDev* gps;
@@ -106,7 +111,7 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
 }
 
 // TRACE: CTA 0 records clock64 at its phase boundaries into p.trace (tools/ozaki_trace.py; BOPL_OZ_TRACE=1), slot layout
-// [row][8]: 0 K* start, 1 K* done, 2 accumulators full, 3 recombined (TMEM released), 4 diagonal solve done, 5 digits published
+// [row][24]: 8.. every compute warp's TMEM release, 16.. every compute warp's K* done; 0 K* start, 1 K* done, 2 accumulators full, 3 recombined (TMEM released), 4 diagonal solve done, 5 digits published
 // (compute warp 2, lane 0); 6 first MMA of the row issued, 7 last MMA of the row committed (MMA thread).  First work item only.
 template <int OS, bool TRACE>
 __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   const uint32_t tmem = tmem_base_s;
   const int nitems = p.m * p.ntiles;
 
-  if (warp == 0) {
+  if (warp == PROD_WARP) {
     // ================================================================ producer: operand k-steps and per-block-row staging
     if (lane == 0) {
       unsigned gc = 0, brow = 0, sc = 0;   // k-steps issued; block rows whose digits were waited for; staging blocks issued
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
       const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
       auto stage_block = [&](const GpDev& g, int i) {
         const unsigned buf = sc & 1;
-        if (sc >= 2) mbar_wait(&sb_empty[buf], ((sc >> 1) - 1) & 1);
+        if (sc >= 2) mbar_wait_backoff(&sb_empty[buf], ((sc >> 1) - 1) & 1, 200);
         mbar_expect_tx(&sb_full[buf], sb_bytes);
         bulk_g2s(SB + (size_t)buf * SBD, g.OzStage + (size_t)i * SBD, sb_bytes, &sb_full[buf]);
         ++sc;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 #pragma unroll 1
         for (int ks = 0; ks < 2; ++ks) {
           const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
-          mbar_wait(&empty_bar[st], (use & 1) ^ 1);
+          mbar_wait_backoff(&empty_bar[st], (use & 1) ^ 1, 100);
           unsigned char* dst = stage_s + (size_t)st * OSTAGE;
           mbar_expect_tx(&full_bar[st], OSTAGE);
           bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           // kb < i-1 (needing neither) are prefetched while the previous block row is still being solved.
           for (int kb = 0; kb + 1 < i; ++kb) load_block(Limg, i, kb);
           if (i > 0) {                        // the newest block: wait until its digits are in the scratch panel
-            mbar_wait(&v_pub, brow & 1);
+            mbar_wait_backoff(&v_pub, brow & 1, 100);
             ++brow;
             asm volatile("fence.proxy.async;\n" ::: "memory");
           }
@@ -191,23 +196,23 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           else if (item + (int)gridDim.x < nitems) stage_block(p.gps[((item + (int)gridDim.x) / p.ntiles) * p.H + p.hsel], 0);
           if (i > 0) load_block(Limg, i, i - 1);
         }
-        mbar_wait(&v_pub, brow & 1);       // the last block row arrives too: keep the phases in step
+        mbar_wait_backoff(&v_pub, brow & 1, 200);       // the last block row arrives too: keep the phases in step
         ++brow;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
       unsigned gc = 0, uu = 0;            // k-steps consumed; accumulator generations started
       const unsigned lboA = 128 * 16, lboB = OS * OB * 16, sbo = 128;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         for (int i = 1; i < nb; ++i) {
-          if (uu > 0) mbar_wait(&tmem_empty, (uu - 1) & 1);     // the previous block row's accumulators have been read
+          if (uu > 0) mbar_wait_backoff(&tmem_empty, (uu - 1) & 1, 50);     // the previous block row's accumulators have been read
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 8 + 6] = clock64();
+          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 24 + 6] = clock64();
           for (int ks2 = 0; ks2 < 2 * i; ++ks2) {
             const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
-            mbar_wait(&full_bar[st], use & 1);
+            mbar_wait_backoff(&full_bar[st], use & 1, 20);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const unsigned lk = smem_u32(stage_s + (size_t)st * OSTAGE), vb = lk + LHALF;
             const uint32_t first = (ks2 == 0) ? 0u : 1u;
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             ++gc;
           }
           umma_commit(&acc_full);
-          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 8 + 7] = clock64();
+          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 24 + 7] = clock64();
           ++uu;
         }
       }
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         const double* scale_s = alpha_s + OB;
 
         const bool tr = TRACE && blockIdx.x == 0 && item == 0 && warp == 2 && lane == 0;
-        if (tr) p.trace[i * 8 + 0] = clock64();
+        if (tr) p.trace[i * 24 + 0] = clock64();
         // ---- K*^T of the block row straight into the fragments (rows in the front padding are masked), mean
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -313,10 +318,11 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         }
 
         // ---- subtract sum_k L_ik V_k: six s32 accumulators per (candidate, row), Horner in 2^-8, then the two power-of-two scales
-        if (tr) p.trace[i * 8 + 1] = clock64();
+        if (tr) p.trace[i * 24 + 1] = clock64();
+        if (TRACE && blockIdx.x == 0 && item == 0 && lane == 0) p.trace[i * 24 + 16 + (warp - 2)] = clock64();     // every warp: K* done
         if (i > 0) {
           mbar_wait(&acc_full, uu & 1);
-          if (tr) p.trace[i * 8 + 2] = clock64();
+          if (tr) p.trace[i * 24 + 2] = clock64();
           ++uu;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
@@ -351,7 +357,8 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty);
         }
-        if (tr) p.trace[i * 8 + 3] = clock64();
+        if (tr) p.trace[i * 24 + 3] = clock64();
+        if (TRACE && blockIdx.x == 0 && item == 0 && lane == 0) p.trace[i * 24 + 8 + (warp - 2)] = clock64();      // every warp: TMEM released
 
         // ---- diagonal block, in registers and in place: V^T[:, nt] = sum_{kt <= nt} rhs^T[:, kt] * Dinv^T[kt, nt]
         {
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb_empty[buf]);
-        if (tr) p.trace[i * 8 + 4] = clock64();
+        if (tr) p.trace[i * 24 + 4] = clock64();
         ++sbc;
 
         // ---- publish the digits of V_i for the later block rows.  Position of row 8 nt + 2 t + e inside the 64-deep block:
@@ -450,7 +457,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           asm volatile("fence.proxy.async;\n" ::: "memory");
         }
         mbar_arrive(&v_pub);
-        if (tr) p.trace[i * 8 + 5] = clock64();
+        if (tr) p.trace[i * 24 + 5] = clock64();
       }
       // ---- finalize the item: the four t-lanes of a candidate hold its partial sums
 #pragma unroll
@@ -712,19 +719,19 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
   p.trace = nullptr;
   if (const char* tf = getenv("BOPL_OZ_TRACE")) {      // diagnostic: phase timestamps of CTA 0's first work item -> text file
     long long* tb = nullptr;
-    const size_t tbytes = (size_t)nb * 8 * sizeof(long long);
+    const size_t tbytes = (size_t)nb * 24 * sizeof(long long);
     BOPL_CUDA(h, cudaMalloc((void**)&tb, tbytes));
     BOPL_CUDA(h, cudaMemsetAsync(tb, 0, tbytes, st));
     p.trace = tb;
     posterior_ozaki_kernel<S, true><<<grid, ONT, smem, st>>>(p);
     BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
-    std::vector<long long> host((size_t)nb * 8);
+    std::vector<long long> host((size_t)nb * 24);
     BOPL_CUDA(h, cudaStreamSynchronize(st));
     BOPL_CUDA(h, cudaMemcpy(host.data(), tb, tbytes, cudaMemcpyDeviceToHost));
     cudaFree(tb);
     if (FILE* f = fopen(tf, "w")) {
       for (int i = 0; i < nb; ++i) {
-        for (int c = 0; c < 8; ++c) fprintf(f, "%lld%c", host[(size_t)i * 8 + c], c == 7 ? '\n' : ' ');
+        for (int c = 0; c < 24; ++c) fprintf(f, "%lld%c", host[(size_t)i * 24 + c], c == 23 ? '\n' : ' ');
       }
       fclose(f);
     }

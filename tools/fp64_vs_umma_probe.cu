@@ -18,7 +18,7 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile("{\n.reg .pred P1;\nW_L:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra W_D;\nbra W_L;\nW_D:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__global__ void __launch_bounds__(288, 1) probe(int mma_reps, int fp_iters, int fp_mode, long long* out) {
+__global__ void __launch_bounds__(288, 1) probe(int mma_reps, int fp_iters, int fp_mode, long long* out, long long* perwarp) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ unsigned long long bar;
   __shared__ uint32_t tmem_base_s;
@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(288, 1) probe(int mma_reps, int fp_iters, int 
     for (int u = 0; u < 8; ++u) s += a[u];
     if (s == 123.456) out[0] = 0;
     if (tid == 32) out[blockIdx.x * 2 + 1] = t1 - t0;
+    if ((tid & 31) == 0 && blockIdx.x == 0 && perwarp) perwarp[warp] = t1 - t0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -82,7 +83,7 @@ int main() {
   CK(cudaSetDevice(0));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   long long* d;
-  CK(cudaMalloc(&d, sms * 16));
+  CK(cudaMalloc(&d, sms * 16 + 16 * 8));
   const size_t sm = (128 + 256) * 128 + 1024;
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   std::vector<long long> h(sms * 2);
@@ -94,8 +95,8 @@ int main() {
       const int mr = (cfg == 0) ? 0 : reps, fi = (cfg == 1) ? 0 : it;
       if (fp_mode == 1 && cfg == 1) continue;
       for (int rep = 0; rep < 2; ++rep) {
-        CK(cudaMemset(d, 0, sms * 16));
-        probe<<<sms, 288, sm>>>(mr, fi, fp_mode, d);
+        CK(cudaMemset(d, 0, sms * 16 + 16 * 8));
+        probe<<<sms, 288, sm>>>(mr, fi, fp_mode, d, d + sms * 2);
         CK(cudaDeviceSynchronize());
       }
       CK(cudaMemcpy(h.data(), d, sms * 16, cudaMemcpyDeviceToHost));
@@ -105,6 +106,11 @@ int main() {
       const char* nm = fp_mode == 0 ? "dfma" : "dmma";
       if (mr) printf(", \"%s_cfg%d_mma_mac_per_clk\": %.0f", nm, cfg, 4.0 * reps * 128 * 256 * 32 / cm);
       if (fi) printf(", \"%s_cfg%d_fp64_fma_lanes_per_clk\": %.1f", nm, cfg, fp_mode == 0 ? 8.0 * 32 * 8 * fi / cf : 8.0 * 4 * 256 * fi / cf);
+      if (fi) {   // clocks of the eight FP64 warps of CTA 0 (warp w sits on sub-partition w % 4; warp 0 issues the MMAs)
+        long long pw[16];
+        CK(cudaMemcpy(pw, d + sms * 2, sizeof(pw), cudaMemcpyDeviceToHost));
+        printf(", \"%s_cfg%d_clocks_warp1to8\": [%lld, %lld, %lld, %lld, %lld, %lld, %lld, %lld]", nm, cfg, pw[1], pw[2], pw[3], pw[4], pw[5], pw[6], pw[7], pw[8]);
+      }
     }
   }
   printf("}\n");

@@ -24,11 +24,13 @@ print("row   K*    wait_acc  recomb  diag  digits | row_total | mma_start-after-
 tot = 0
 for i in range(len(t)):
     r = t[i]
-    kst, kdone, accf, rec, diag, pub, m0, m1 = r
+    kst, kdone, accf, rec, diag, pub, m0, m1 = r[:8]
     if i == 0:
         print("%3d %6d %8s %7s %6d %6d | %8d" % (i, kdone - kst, "-", "-", diag - rec, pub - diag, pub - kst))
         continue
     prev_pub = t[i - 1, 5]
     print("%3d %6d %8d %7d %6d %6d | %8d | mma: start %+7d after prev recomb, busy %6d, done %+6d vs K* done"
           % (i, kdone - kst, accf - kdone, rec - accf, diag - rec, pub - diag, pub - prev_pub, m0 - t[i - 1, 3], m1 - m0, m1 - kdone))
+    print("      K* done per warp (vs warp 2):", " ".join("%+6d" % (x - kdone) for x in r[16:24]), "| TMEM released per warp (vs warp 2):",
+          " ".join("%+6d" % (x - rec) for x in r[8:16]), "| mma start vs LAST release %+6d" % ((t[i + 1, 6] - max(r[8:16])) if i + 1 < len(t) else 0))
 print("item total clocks:", t[-1, 5] - t0)
