@@ -148,6 +148,22 @@ def test_int8_uei_values_and_argmax():
     assert np.array_equal(np.argsort(-a8, kind="stable")[:20], np.argsort(-a64, kind="stable")[:20])
 
 
+def test_int8_posterior_many_block_rows():
+    """n = 3000 (47 block rows of 64, front padding 8): more block rows, longer accumulation chains and larger accumulators than
+    the benchmark shape; 6- and 7-digit kernels against the fp64 kernel and the oracle."""
+    p = make_problem("S", n=3000, N=400)
+    om = oracle_model(p)
+    mu_o, v_o = om.predict(p["Xc"])
+    g64 = gpu_model(p, gradients=False)
+    mu_d, v_d = g64.predict(p["Xc"])
+    for kernel, tol in (("int8", 2e-10), ("int8x7", 2e-12)):
+        gm = gpu_model(p, gradients=False, posterior_kernel=kernel)
+        mu_g, v_g = gm.predict(p["Xc"])
+        check_close(mu_g, mu_o, "n=3000 mean")
+        assert rel_err(v_g, v_o) < RTOL, (kernel, rel_err(v_g, v_o))
+        assert rel_err(v_g, v_d) < tol, (kernel, rel_err(v_g, v_d))
+
+
 def test_int8_kernel_selection_rules():
     from bopl_b200._lib import BoplError
     p = make_problem("portfolio1", n=80, N=50)

@@ -80,7 +80,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 
 // One CTA of 128 threads.  A image [128 x K], B image [N x K] (canonical layout, K a multiple of 32).  reps > 1: rate mode.
-__global__ void __launch_bounds__(128, 1) umma_kernel(const int8_t* Aimg, const int8_t* Bimg, int N, int K, int reps, int sync_every, int32_t* out) {
+__global__ void __launch_bounds__(128, 1) umma_kernel(const int8_t* Aimg, const int8_t* Bimg, int N, int K, int reps, int sync_every, int32_t* out, int rotate = 1) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ unsigned long long bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -115,10 +115,13 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(const int8_t* Aimg, const 
       bd[ks] = make_desc(b0 + ks * 2 * lboB, lboB, sbo);
     }
     const int nks = K / 32;
+    uint32_t toff[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) toff[ks] = (uint32_t)((ks % rotate) * N);   // rotate divides 4: the offset depends on ks only
     for (int r = 0; r < reps; ++r) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        if (ks < nks) mma_i8(tmem, ad[ks], bd[ks], idesc, (ks > 0 || r > 0) ? 1u : 0u);   // rate mode keeps accumulating (s32 wraps)
+        if (ks < nks) mma_i8(tmem + toff[ks], ad[ks], bd[ks], idesc, (ks > 0 || r > 0) ? 1u : 0u);   // rate mode keeps accumulating (s32 wraps); rotate > 1: consecutive MMAs hit different accumulators
       if (sync_every > 0 && (r + 1) % sync_every == 0 && r + 1 < reps) {   // optional rendezvous (drains the MMA pipe)
         mma_commit(&bar[1]);
         mbar_wait(&bar[1], (((r + 1) / sync_every - 1) & 1));
@@ -198,6 +201,20 @@ int main() {
       CK(cudaEventElapsedTime(&ms, e0, e1));
       const double ops = 2.0 * 128 * N * K * (double)reps * sms;
       printf(", \"int8_tops_N%d_sync%d\": %.1f", N, sync_every, ops / (ms * 1e-3) / 1e12);
+    }
+    // consecutive instructions on DIFFERENT accumulator column ranges (independent): is the small-N rate a dependent-accumulate latency?
+    for (int rotate : {2, 4}) {
+      if (N * rotate > 512) continue;
+      umma_kernel<<<sms, 128, sm>>>(dA, dB, N, K, 64, 0, nullptr, rotate);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      umma_kernel<<<sms, 128, sm>>>(dA, dB, N, K, reps, 0, nullptr, rotate);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double ops = 2.0 * 128 * N * K * (double)reps * sms;
+      printf(", \"int8_tops_N%d_rotate%d\": %.1f", N, rotate, ops / (ms * 1e-3) / 1e12);
     }
     cudaFree(dA);
     cudaFree(dB);
