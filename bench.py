@@ -291,7 +291,10 @@ def run_gpu(args):
                                    % (w["n"], N, w["n_w"], w["L"], args.utility, K_ANCHOR),
                        "posterior_kernel": args.posterior,
                        "sharding": "candidates row-sharded, %d per rank; all-gather of top-%d records only" % (N, K_ANCHOR),
-                       "l2": "working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2, and a 256 MB flush write between steps"},
+                       "l2": ("working set (L 3x33.5 MB + V panels 310 MB + candidates 84 MB) > 126 MB L2, and a 256 MB flush write between steps"
+                              if args.posterior == "fp64" else
+                              "working set (factor digit images 3x%.1f MB + solved-digit panels %d MB + candidates 84 MB) > 126 MB L2, "
+                              "and a 256 MB flush write between steps" % ((12.2, 232) if args.posterior == "int8" else (14.2, 271)))},
             "clocks": sampler.summary(),
             "e2e": {"value": evals_per_step / float(e2e_t.item()), "unit": UNIT,
                     "h2d_bytes_per_step": int(N * d * 8 + (p["Z"].size + theta.size + 2 * len(theta)) * 8),
