@@ -313,6 +313,42 @@ def main():
             print("wrote uEI_affine_%s.npz" % name)
 
 
+BIG_CASES = [  # several 64-row block rows and more candidates than the small-batch limit: the blocked posterior kernels' own regime
+    ("S", dict(N=200, n=300, n_w=8, L=4, H=1), "test_dtlz1a_linear.py"),
+    ("dtlz2a_quad", dict(N=150, n=200, n_w=6, L=8, H=1), "test_dtlz2a_quad.py"),
+]
+
+
+def main_big():
+    """Value path only (posterior + uEI values) at sizes where the blocked posterior kernels do block-row updates: big_*.npz."""
+    from bopl_b200.synthetic import make_problem
+    R = build_reference()
+    for name, kw, script in BIG_CASES:
+        p = make_problem(name, **kw)
+        model = reference_model(R, p)
+        func, grad = R.exp_utils(script, p["m"])
+        theta = p["theta"]
+        if p["use_full_support"]:
+            dist = R.UtilityDistribution(support=theta, prob_dist=np.array(p["prob"]), utility_func=func)
+        else:
+            dist = R.UtilityDistribution(prior_sample_generator=lambda n_s, seed=None: theta[:n_s], utility_func=func,
+                                         use_full_support=False)
+        util = R.Utility(func=func, gradient=grad, parameter_distribution=dist)
+        X = p["Xc"]
+        out = dict(name=name, acq="big", N=kw["N"], n=kw["n"], n_w=kw["n_w"], L=kw["L"], H=kw["H"])
+        model.set_hyperparameters(0)
+        out["mean"], out["var"] = model.predict(X)
+        _, out["var_noiseless"] = model.predict_noiseless(X)
+        acq = R.uEI(model, None, optimizer=None, utility=util)
+        acq.W_samples = p["Z"].copy()
+        acq.utility_parameter_samples = theta
+        acq.number_of_gp_hyps_samples = p["H"]
+        model.set_hyperparameters(0)
+        out["acq_sequential"] = acq._compute_acq(X, parallel=False)
+        np.savez(os.path.join(HERE, "big_%s.npz" % name), **out)
+        print("wrote big_%s.npz  var range [%.3e, %.3e]  acq max %.3e" % (name, out["var"].min(), out["var"].max(), out["acq_sequential"].max()))
+
+
 CONSTRAINED_CASES = [  # (problem name, kwargs): m = 2 uses the reference's own callable of experiments/test_portfolio2.py
     ("dtlz1a_linear", dict(N=40, n=30, L=5, H=2, utility="constrained")),       # m = 2: one constraint
     ("vlmop3_exp", dict(N=40, n=30, L=5, H=1, utility="constrained")),          # m = 3: two constraints
@@ -519,7 +555,7 @@ def main_thompson(T=14):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        {"main": main, "constrained": main_constrained, "marginal": main_marginal, "thompson": main_thompson}[sys.argv[1]]()
+        {"main": main, "big": main_big, "constrained": main_constrained, "marginal": main_marginal, "thompson": main_thompson}[sys.argv[1]]()
     else:
         main()
         main_constrained()

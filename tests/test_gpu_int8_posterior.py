@@ -148,6 +148,27 @@ def test_int8_uei_values_and_argmax():
     assert np.array_equal(np.argsort(-a8, kind="stable")[:20], np.argsort(-a64, kind="stable")[:20])
 
 
+@pytest.mark.parametrize("kernel", ["fp64"] + KERNELS)
+@pytest.mark.parametrize("fname", ["big_S.npz", "big_dtlz2a_quad.npz"])
+def test_blocked_kernels_against_reference_generated_golden(fname, kernel):
+    """All three posterior kernels against outputs of the reference's OWN code (tests/golden/make_golden.py big) at sizes where they do
+    block-row updates (n = 300 / 200, N = 200 / 150): mean, variance (+ noiseless), uEI values, argmax — not via the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname), allow_pickle=False)
+    p = make_problem(str(g["name"]), N=int(g["N"]), n=int(g["n"]), n_w=int(g["n_w"]), L=int(g["L"]), H=int(g["H"]))
+    gm = gpu_model(p, gradients=False, posterior_kernel=kernel)
+    om = oracle_model(p)                                    # only for the conditioning floor of the tolerance
+    floor = variance_floor(om, p["Xc"])
+    extra = ABS6 * p["variance"][:, 0][:, None] if kernel == "int8" else 0.0
+    mu, var = gm.predict(p["Xc"])
+    check_close(mu, g["mean"], fname + " mean")
+    assert np.all(np.abs(var - g["var"]) <= RTOL * np.abs(g["var"]) + 64 * floor + extra), np.max(np.abs(var - g["var"]) / np.abs(g["var"]))
+    assert np.all(np.abs(gm.predict_noiseless(p["Xc"])[1] - g["var_noiseless"]) <= RTOL * np.abs(g["var"]) + 64 * floor + extra)
+    a = gpu_acquisition(p, gm)._compute_acq(p["Xc"])
+    check_close(a, g["acq_sequential"], fname + " uEI")
+    assert np.argmax(a) == np.argmax(g["acq_sequential"])
+
+
 def test_int8_posterior_many_block_rows():
     """n = 3000 (47 block rows of 64, front padding 8): more block rows, longer accumulation chains and larger accumulators than
     the benchmark shape; 6- and 7-digit kernels against the fp64 kernel and the oracle."""
