@@ -27,6 +27,9 @@
 // subtracted, inverted diagonal block applied in place on DMMA, mean and sum V^2, digits of the solved block published.
 // The FP64 pipe and the int8 tensor pipe time-share on this part (tools/fp64_vs_umma_probe.cu), so the launch costs about
 // (tensor time) + (fp64 time); profiles/r01_summary.md §A has the measurements.
+#include <atomic>
+#include <thread>
+
 #include "pipeline.cuh"
 
 namespace bopl {
@@ -513,24 +516,33 @@ void ozaki_prepare(const double* Lp, int n_pad, int S, std::vector<signed char>&
       scale[R] = std::ldexp(1.0, e + 1);   // >= 2 mx: digits of x / scale stay within +-2^(8S-2) / 2^(8S-1)
     }
   }
-  for (int i = 1; i < nb; ++i)
-    for (int kb = 0; kb < i; ++kb) {
-      signed char* base = img.data() + ((size_t)i * (i - 1) / 2 + kb) * limg;
-      for (int r = 0; r < OB; ++r) {
-        const int R = i * OB + r;
-        const double inv = 1.0 / scale[R];
-        for (int k = 0; k < OB; ++k) {
-          const int kp = 16 * ((k % 8) / 2) + 2 * (k / 8) + (k % 2);
-          long long t = std::llrint(std::ldexp(Lp[(size_t)R * n_pad + kb * OB + k] * inv, 8 * S - 1));
-          for (int s = S - 1; s >= 0; --s) {
-            const int dg = (int)((t + 128) & 255) - 128;
-            t = (t - dg) >> 8;
-            const int rr = s * OB + r;
-            base[((size_t)(kp / 16) * (S * OB / 8) + rr / 8) * 128 + (rr % 8) * 16 + (kp % 16)] = (signed char)dg;
+  // the block rows are independent: spread them over the host cores (largest first)
+  std::atomic<int> next(nb - 1);
+  auto work = [&]() {
+    for (int i = next.fetch_sub(1); i >= 1; i = next.fetch_sub(1))
+      for (int kb = 0; kb < i; ++kb) {
+        signed char* base = img.data() + ((size_t)i * (i - 1) / 2 + kb) * limg;
+        for (int r = 0; r < OB; ++r) {
+          const int R = i * OB + r;
+          const double inv = 1.0 / scale[R];
+          for (int k = 0; k < OB; ++k) {
+            const int kp = 16 * ((k % 8) / 2) + 2 * (k / 8) + (k % 2);
+            long long t = std::llrint(std::ldexp(Lp[(size_t)R * n_pad + kb * OB + k] * inv, 8 * S - 1));
+            for (int s = S - 1; s >= 0; --s) {
+              const int dg = (int)((t + 128) & 255) - 128;
+              t = (t - dg) >> 8;
+              const int rr = s * OB + r;
+              base[((size_t)(kp / 16) * (S * OB / 8) + rr / 8) * 128 + (rr % 8) * 16 + (kp % 16)] = (signed char)dg;
+            }
           }
         }
       }
-    }
+  };
+  const int nthr = std::max(1, std::min<int>(nb - 1, (int)std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
 }
 
 // Per-block-row staging array of the kernel: [n_pad/64][36 Dinv B fragments (64 doubles each) | Xs^T [d][64] | alpha[64] | scale[64]].
