@@ -286,9 +286,9 @@ def run_gpu(args):
         out = {
             "metric": METRIC, "value": evals_per_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.posterior == "fp64" else
-                     "f64 (the triangular solve's n^2/2 update as exact int8 digit products with s32 accumulation, %d-bit operands; everything else f64)"
-                     % (47 if args.posterior == "int8" else 55),
+            "dtype": "f64",
+            "dtype_note": "every result is f64; with --posterior int8 / int8x7 the triangular solve's n^2/2 update is carried out as exact int8 "
+                          "digit products with s32 accumulation on 47- / 55-bit fixed-point splits of its f64 operands (DESIGN.md 3.1b)",
             "data": "synthetic",
             "config": {"workload": "S: d=10 m=3 n=%d N=%d candidates per GPU, n_w=%d L=%d H=1 Matern52-ARD noise=1e-6 %s utility, top-%d anchors"
                                    % (w["n"], N, w["n_w"], w["L"], args.utility, K_ANCHOR),
