@@ -279,6 +279,14 @@ def run_gpu(args):
                                         "note": "the same algorithmic fp64 flops against the cuBLAS DGEMM peak the fp64 kernel is bound by"},
                     "peak_source": "profiles/r01_int8_peaks.json: back-to-back tcgen05.mma kind::i8 M=128 N=256 K=32 on all SMs "
                                    "(tools/int8_umma_probe.cu); the FP64 pipe time-shares with it (profiles/r01_fp64_vs_int8.json)"}
+            # The FP64 pipe and the int8 tensor pipe time-share on this part (profiles/r01_fp64_vs_int8.json), so the launch is bounded by the
+            # SUM of its int8 time at the int8 peak and its fp64 time at the fp64 peak: K*, mean, square-sum and the 64-row diagonal solves
+            # stay in fp64 (m N [64 n + 4 n + n (3d + c_K)] flops), the rest of the n^2 triangular solve runs as digit products.
+            fp64_part = m * float(N) * (64.0 * w["n"] + 4.0 * w["n"] + w["n"] * (3 * d + C_K))
+            t_i8, t_f64 = int8_ops / (peak_i8 * 1e12) * 1e3, fp64_part / (float(peaks["microbench"]["dmma_acc8_tpb256_tflops"]) * 1e12) * 1e3
+            roof["time_shared_bound"] = {"int8_ms": t_i8, "fp64_ms": t_f64, "bound_ms": t_i8 + t_f64, "frac": (t_i8 + t_f64) / trsm_ms_avg,
+                                         "fp64_flops_per_launch": fp64_part, "fp64_peak": float(peaks["microbench"]["dmma_acc8_tpb256_tflops"]),
+                                         "note": "measured launch time against (int8 ops at the int8 peak) + (fp64 flops at the DMMA issue peak, the higher of the two fp64 peaks)"}
             if fp64_ms is not None:
                 roof["fp64_kernel"] = {"kernel": "posterior_trsm_t_kernel", "kernel_ms": fp64_ms,
                                        "frac_of_dgemm_peak": flops_launch / (fp64_ms * 1e-3) * 1e-12 / peak_tf,
