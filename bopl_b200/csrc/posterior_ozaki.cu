@@ -7,9 +7,9 @@
 // substitution V_i = Dinv_i (K*_i - sum_{k<i} L_ik V_k), 64-row blocks, tile = 128 candidates, then mean / variance.
 // What changes is the update sum_k L_ik V_k (n^2/2 FMAs per candidate, 97 % of the work).  sm_100a has no fp64 tcgen05 kind,
 // but its int8 kind is 128x faster than the fp64 pipe, and an fp64 product can be split into exact int8 products:
-//   * every row of the off-diagonal part of L is scaled by a power of two ls_r >= 2 max|L_rk| and written in S = 6 (or 7) balanced
+//   * every row of the off-diagonal part of L is scaled by the smallest power of two ls_r >= max|L_rk| / 0.995 and written in S = 6 (or 7) balanced
 //     base-256 digits (int8): L_rk = ls_r * sum_s d_s 2^(-7-8s)  (47 / 55 fractional bits; once per model, host or device);
-//   * |V| <= sqrt(variance) (because var = variance - |V|^2 >= 0), so V is written in fixed point against vs = 2^ceil(log2 sigma)+1
+//   * |V| <= sqrt(variance) (because var = variance - |V|^2 >= 0), so V is written in fixed point against vs = 2^ceil(log2(sigma / 0.995))
 //     the same way, on the fly, by the warp that solved it;
 //   * digit products are accumulated EXACTLY in s32 by the tensor core, one accumulator per digit weight g = s_L + s_V < S
 //     (|acc| <= S * n * 2^14 < 2^31 for n <= 16384), and combined once per block row in fp64.
@@ -38,6 +38,8 @@ namespace {
 
 constexpr int OB = 64;                       // rows per block row
 constexpr int OZ_MAXD = 12;                  // input dimensions the shared-memory plan is sized for
+// S balanced base-256 digits hold |t| <= 127 (256^S - 1) / 255 = 0.498 * 2^(8S): a value may use up to OZ_FILL of its power-of-two scale
+constexpr double OZ_FILL = 0.995;
 constexpr int VPL = 128 * 32;                // 4096 B: one digit plane of V, 128 candidates x 32 k
 // S = digits per operand: 6 (47 fractional bits; 21 digit pairs) or 7 (55 bits, i.e. every bit of an fp64 mantissa; 28 pairs)
 template <int S>
@@ -251,10 +253,10 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
       const GpDev& gp = p.gps[j * p.H + p.hsel];
       const int kind = gp.kind;
       const double variance = gp.variance;
-      const double vs = exp2(ceil(log2(sqrt(variance))) + 1.0);  // fixed-point scale of V: |V| <= sigma <= vs / 2
+      const double vs = exp2(ceil(log2(sqrt(variance) * (1.0 / OZ_FILL))));   // fixed-point scale of V: |V| <= sigma <= OZ_FILL vs
       const double to_fix = (OS == 6 ? 140737488355328.0 : 36028797018963968.0) / vs;   // 2^47 / vs (2^55 / vs)
       const double from_fix16 = vs * (1.0 / 1073741824.0);       // vs 2^-14 (digit product weight) 2^-16 (integer Horner)
-      const double vmax = 0.5 * vs;
+      const double vmax = OZ_FILL * vs;
       __syncwarp();
       for (int idx = lane; idx < 16 * d; idx += 32) {
         const int c = idx / d, q = idx - c * d;
@@ -512,8 +514,8 @@ void ozaki_prepare(const double* Lp, int n_pad, int S, std::vector<signed char>&
     for (int k = 0; k < i * OB; ++k) mx = std::max(mx, std::fabs(Lp[(size_t)R * n_pad + k]));
     if (mx > 0.0) {
       int e;
-      std::frexp(mx, &e);                  // mx = f 2^e, 0.5 <= f < 1  ->  2^e > mx
-      scale[R] = std::ldexp(1.0, e + 1);   // >= 2 mx: digits of x / scale stay within +-2^(8S-2) / 2^(8S-1)
+      const double f = std::frexp(mx, &e);                       // mx = f 2^e, 0.5 <= f < 1
+      scale[R] = std::ldexp(1.0, f <= OZ_FILL ? e : e + 1);       // |x| / scale <= OZ_FILL: the digits of x / scale 2^(8S-1) fit
     }
   }
   // the block rows are independent: spread them over the host cores (largest first)
@@ -593,7 +595,7 @@ struct OzPrep {
   double* stage;
 };
 
-// power-of-two row scales (>= 2 max |L_Rk| over the columns left of the row's 64 x 64 diagonal block).  grid (n_pad / 8, G) x 256
+// power-of-two row scales (smallest with max |L_Rk| <= OZ_FILL scale, over the columns left of the row's 64 x 64 diagonal block).  grid (n_pad / 8, G) x 256
 __global__ void oz_scale_kernel(const OzPrep* pp, int n_pad, int d) {
   const OzPrep& q = pp[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, R = blockIdx.x * 8 + warp;
@@ -604,7 +606,8 @@ __global__ void oz_scale_kernel(const OzPrep* pp, int n_pad, int d) {
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) {
     const int E = (__double2hiint(mx) >> 20) & 0x7ff;      // mx = 1.f 2^(E-1023) = 0.1f 2^(E-1022): frexp exponent E - 1022
-    const double sc = (mx > 0.0 && E > 0) ? __hiloint2double((E + 2) << 20, 0) : 1.0;   // 2^(E - 1022 + 1)
+    const double p2 = __hiloint2double((E + 1) << 20, 0);  // 2^(E - 1022) > mx
+    const double sc = (mx > 0.0 && E > 0) ? (mx <= OZ_FILL * p2 ? p2 : 2.0 * p2) : 1.0;   // as ozaki_prepare
     q.stage[(size_t)(R / OB) * oz_sb_doubles(d) + NFRAG * 64 + (d + 1) * OB + (R % OB)] = sc;
   }
 }

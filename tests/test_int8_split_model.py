@@ -32,7 +32,7 @@ def digits_bias(t, S):
 @pytest.mark.parametrize("S", [6, 7])
 def test_digit_split_is_exact_and_both_forms_agree(S):
     rs = np.random.RandomState(S)
-    lim = 2 ** (8 * S - 2)                                   # |x| / scale <= 1/2  ->  |t| <= 2^(8S-2)
+    lim = int(0.995 * 2 ** (8 * S - 1))                      # |x| / scale <= 0.995 (OZ_FILL)  ->  |t| <= 0.995 2^(8S-1) < 127 (256^S - 1) / 255
     t = rs.randint(-lim, lim + 1, size=20000, dtype=np.int64)
     t[:6] = [0, 1, -1, lim, -lim, 127]
     d1, d2 = digits_sequential(t, S), digits_bias(t, S)
@@ -46,11 +46,11 @@ def test_magic_number_rounding_matches_llrint():
     """6 digits: fma(v, 2^47 / vs, 1.5 * 2^52) leaves round-to-nearest-even(v 2^47 / vs) in the low mantissa bits."""
     rs = np.random.RandomState(1)
     vs = 4.0
-    v = rs.uniform(-0.5 * vs, 0.5 * vs, size=50000)
+    v = rs.uniform(-0.995 * vs, 0.995 * vs, size=50000)
     z = v * (2.0 ** 47 / vs) + 6755399441055744.0            # the product is exact (power-of-two scale): one rounding, as in the FMA
     t = z.view(np.int64) - np.int64(0x4338000000000000)
     assert np.array_equal(t, np.rint(v * (2.0 ** 47 / vs)).astype(np.int64))
-    assert np.abs(t).max() <= 2 ** 46
+    assert np.abs(t).max() <= 2 ** 47
 
 
 def test_k_permutation_is_a_bijection_and_thread_rows_are_contiguous():
@@ -74,9 +74,10 @@ def test_accumulated_digit_products_reproduce_the_dot_product(S):
     n = 16384
     L = rs.standard_normal(n) * np.exp(rs.uniform(-6, 0, size=n))
     V = rs.standard_normal(n)
-    ls = 2.0 ** (np.frexp(np.abs(L).max())[1] + 1)
+    f, e = np.frexp(np.abs(L).max())
+    ls = 2.0 ** (e if f <= 0.995 else e + 1)                  # ozaki_prepare: smallest power of two with max|L| <= 0.995 ls
     sigma = np.abs(V).max()
-    vs = 2.0 ** (np.ceil(np.log2(sigma)) + 1)
+    vs = 2.0 ** np.ceil(np.log2(sigma / 0.995))
     tl = np.rint(np.ldexp(L / ls, 8 * S - 1)).astype(np.int64)
     tv = np.rint(np.ldexp(V / vs, 8 * S - 1)).astype(np.int64)
     dl, dv = digits_sequential(tl, S), digits_sequential(tv, S)
