@@ -14,7 +14,7 @@
 //   * digit products are accumulated EXACTLY in s32 by the tensor core, one accumulator per digit weight g = s_L + s_V < S
 //     (|acc| <= S * n * 2^14 < 2^31 for n <= 16384), and combined once per block row in fp64.
 // Dropped terms (g >= S) are below 2^(-8S) of ls_r * vs * n: measured against the fp64 kernel on 2^20 candidates of the benchmark
-// shape, 3.4e-11 relative on the variance with 6 digits and 2.9e-13 with 7 (tests/test_gpu_int8_posterior.py).
+// shape, 1.9e-11 relative on the variance with 6 digits and 1.4e-13 with 7 (tests/test_gpu_int8_posterior.py).
 //
 // One instruction covers several digit pairs: the S digit planes of an L block are stacked as ONE 64 S-row B operand, so
 // V digit a against L digits 0..S-1-a is a single N = 64 (S - a) MMA (split at N = 256) whose output columns are exactly the

@@ -5,7 +5,7 @@ with the n^2/2 update of the triangular solve carried out as exact int8 digit pr
 Tolerances.  The split keeps 47 (6 digits) or 55 (7 digits) fractional bits of every operand against a power-of-two scale
 (row maximum of L, prior standard deviation for V), so its error is ABSOLUTE in units of the prior variance:
   * 7 digits: the same tolerance as the fp64 kernel (1e-9 relative + 64 x the oracle's own one-ulp-of-K* sensitivity);
-  * 6 digits: that, plus 1e-10 * prior variance (measured: 2e-11 at the benchmark shape n = 2000, 1e-12 at n = 300).
+  * 6 digits: that, plus 1e-10 * prior variance (measured: 2e-11 at the benchmark shape n = 2000, 6e-13 at n = 300).
 Mean, acquisition values, argmax: as for the fp64 kernel (1e-9 of scale, identical argmax)."""
 import numpy as np
 import pytest
