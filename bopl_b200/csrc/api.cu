@@ -157,6 +157,7 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
   if (const char* v = getenv("BOPL_OZAKI")) h->use_ozaki = atoi(v);
+  if (const char* v = getenv("BOPL_OZ_CLUSTER")) h->oz_cluster = atoi(v);
   if (const char* v = getenv("BOPL_OZAKI_DIGITS")) h->oz_digits = atoi(v) == 7 ? 7 : 6;
   if (const char* v = getenv("BOPL_POSTERIOR")) {        // "fp64" (default), "int8" (6 digits), "int8x7"
     const std::string k(v);

@@ -83,6 +83,7 @@ struct bopl_handle {
   void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
   int use_ozaki = 0;                   // BOPL_OZAKI=1: bopl_set_model also builds the int8 digit images (posterior_ozaki.cu)
   bool has_oz = false;
+  int oz_cluster = 1;                  // BOPL_OZ_CLUSTER=0 disables: CTA pairs sharing the factor's digit images by multicast (posterior_ozaki.cu)
   int oz_digits = 6;                   // digits of the model's images (fixed at upload): 6 = 47 fractional bits, 7 = 55
   void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem[2] = {0, 0};
   size_t hsmall_cap = 0;

@@ -95,6 +95,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n" ::"l"((unsigned long long)smem_u32(bar)) : "memory");
 }
+// arrive on the mbarrier at this offset in both CTAs of the pair when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
+  const unsigned short mask = 3;
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -108,6 +113,13 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsign
                "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
+// the same into this CTA and its cluster peer (same CTA-relative destination and mbarrier offsets in both)
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  const unsigned short mask = 3;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask), "l"(pol)
+               : "memory");
+}
 // 16 TMEM lanes x 8 columns: lane l/4 (+8), columns 2 (l%4), 2 (l%4) + 1 — the C-fragment layout of an 8x8 DMMA tile pair
 __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];\n"
@@ -118,7 +130,10 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
 // TRACE: CTA 0 records clock64 at its phase boundaries into p.trace (tools/ozaki_trace.py; BOPL_OZ_TRACE=1), slot layout
 // [row][24]: 8.. every compute warp's TMEM release, 16.. every compute warp's K* done; 0 K* start, 1 K* done, 2 accumulators full, 3 recombined (TMEM released), 4 diagonal solve done, 5 digits published
 // (compute warp 2, lane 0); 6 first MMA of the row issued, 7 last MMA of the row committed (MMA thread).  First work item only.
-template <int OS, bool TRACE>
+// CL: launched as clusters of two CTAs that walk the same (attribute, block row, block) sequence on neighbouring candidate tiles and share
+// the factor's digit images: each CTA fetches half of every L k-step and multicasts it into both shared memories (the MMA phase is bound
+// by the L2 -> SM bandwidth: 36.9 KB per k-step and SM; the pair needs 30.7 KB).  A ring stage is free when BOTH CTAs' MMAs have read it.
+template <int OS, bool TRACE, bool CL>
 __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   constexpr int LIMG = Oz<OS>::LIMG, LHALF = Oz<OS>::LHALF, VHALF = Oz<OS>::VHALF, VIMG = Oz<OS>::VIMG, OSTAGE = Oz<OS>::OSTAGE,
                 ONSTAGE = Oz<OS>::ONSTAGE;
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   if (tid == 0) {
     for (int s = 0; s < ONSTAGE; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sb_full[s], 1);
@@ -155,7 +170,16 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  const int nitems = p.m * p.ntiles;
+  // work items: (attribute, candidate tile), or for a cluster (attribute, pair of tiles) with CTA rank r on tile 2 pair + r (a tile past the
+  // end, when their number is odd, is computed on clamped candidates and written nowhere)
+  unsigned crank = 0;
+  if (CL) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");   // the peer's barriers are initialised
+  }
+  const int tpi = CL ? (p.ntiles + 1) / 2 : p.ntiles;          // tiles (tile pairs) per attribute
+  const int nitems = p.m * tpi;
+  const int item0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, istep = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == PROD_WARP) {
     // ================================================================ producer: operand k-steps and per-block-row staging
@@ -178,15 +202,20 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           mbar_wait_backoff(&empty_bar[st], (use & 1) ^ 1, 100);
           unsigned char* dst = stage_s + (size_t)st * OSTAGE;
           mbar_expect_tx(&full_bar[st], OSTAGE);
-          bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
+          if (CL) {      // this CTA's half (one 16-deep k-chunk of all planes) of the L k-step, into both CTAs of the pair
+            bulk_g2s_mc(dst + (size_t)crank * (LHALF / 2), Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF + (size_t)crank * (LHALF / 2),
+                        LHALF / 2, &full_bar[st], pol_keep);
+          } else {
+            bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
+          }
           bulk_g2s_hint(dst + LHALF, Vpanel + (size_t)kb * VIMG + (size_t)ks * VHALF, VHALF, &full_bar[st], vpol);
           ++gc;
         }
       };
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const GpDev& gp = p.gps[(item / p.ntiles) * p.H + p.hsel];
+      for (int item = item0; item < nitems; item += istep) {
+        const GpDev& gp = p.gps[(item / tpi) * p.H + p.hsel];
         const signed char* Limg = gp.OzL;
-        if (item == (int)blockIdx.x) stage_block(gp, 0);
+        if (item == item0) stage_block(gp, 0);
         for (int i = 0; i < nb; ++i) {
           // The staging block of row i+1 reuses the buffer of row i-1, free once that row's diagonal solve is over — which is
           // before its digits are published: issue it behind the wait for those digits, so that the k-steps of the blocks
@@ -198,7 +227,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
             asm volatile("fence.proxy.async;\n" ::: "memory");
           }
           if (i + 1 < nb) stage_block(gp, i + 1);
-          else if (item + (int)gridDim.x < nitems) stage_block(p.gps[((item + (int)gridDim.x) / p.ntiles) * p.H + p.hsel], 0);
+          else if (item + istep < nitems) stage_block(p.gps[((item + istep) / tpi) * p.H + p.hsel], 0);
           if (i > 0) load_block(Limg, i, i - 1);
         }
         mbar_wait_backoff(&v_pub, brow & 1, 200);       // the last block row arrives too: keep the phases in step
@@ -210,11 +239,11 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     if (lane == 0) {
       unsigned gc = 0, uu = 0;            // k-steps consumed; accumulator generations started
       const unsigned lboA = 128 * 16, lboB = OS * OB * 16, sbo = 128;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int item = item0; item < nitems; item += istep) {
         for (int i = 1; i < nb; ++i) {
           if (uu > 0) mbar_wait_backoff(&tmem_empty, (uu - 1) & 1, 50);     // the previous block row's accumulators have been read
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 24 + 6] = clock64();
+          if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 6] = clock64();
           for (int ks2 = 0; ks2 < 2 * i; ++ks2) {
             const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
             mbar_wait_backoff(&full_bar[st], use & 1, 20);
@@ -232,11 +261,12 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
               umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols > 256 ? 256 : ncols), acc_flag);
               if (ncols > 256) umma_i8(tmem + 64 * a + 256, ad, bh, idesc_s8(ncols - 256), acc_flag);
             }
-            umma_commit(&empty_bar[st]);
+            if (CL) umma_commit_pair(&empty_bar[st]);
+            else umma_commit(&empty_bar[st]);
             ++gc;
           }
           umma_commit(&acc_full);
-          if (TRACE && blockIdx.x == 0 && item == 0) p.trace[i * 24 + 7] = clock64();
+          if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 7] = clock64();
           ++uu;
         }
       }
@@ -248,8 +278,8 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     const int cbase = 32 * (warp & 3) + 16 * ((warp - 2) >> 2);   // TMEM lanes of this warp: quadrant warp % 4, half (warp-2)/4
     const uint32_t trow = tmem + ((uint32_t)cbase << 16);
     unsigned uu = 0, sbc = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int j = item / p.ntiles, tile = item - j * p.ntiles;
+    for (int item = item0; item < nitems; item += istep) {
+      const int j = item / tpi, tile = CL ? 2 * (item - j * tpi) + (int)crank : item - j * tpi;
       const GpDev& gp = p.gps[j * p.H + p.hsel];
       const int kind = gp.kind;
       const double variance = gp.variance;
@@ -275,7 +305,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         const double* alpha_s = xt_s + d * OB;
         const double* scale_s = alpha_s + OB;
 
-        const bool tr = TRACE && blockIdx.x == 0 && item == 0 && warp == 2 && lane == 0;
+        const bool tr = TRACE && blockIdx.x == 0 && item == item0 && warp == 2 && lane == 0;
         if (tr) p.trace[i * 24 + 0] = clock64();
         // ---- K*^T of the block row straight into the fragments (rows in the front padding are masked), mean
 #pragma unroll
@@ -324,7 +354,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 
         // ---- subtract sum_k L_ik V_k: six s32 accumulators per (candidate, row), Horner in 2^-8, then the two power-of-two scales
         if (tr) p.trace[i * 24 + 1] = clock64();
-        if (TRACE && blockIdx.x == 0 && item == 0 && lane == 0) p.trace[i * 24 + 16 + (warp - 2)] = clock64();     // every warp: K* done
+        if (TRACE && blockIdx.x == 0 && item == item0 && lane == 0) p.trace[i * 24 + 16 + (warp - 2)] = clock64();     // every warp: K* done
         if (i > 0) {
           mbar_wait(&acc_full, uu & 1);
           if (tr) p.trace[i * 24 + 2] = clock64();
@@ -363,7 +393,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           if (lane == 0) mbar_arrive(&tmem_empty);
         }
         if (tr) p.trace[i * 24 + 3] = clock64();
-        if (TRACE && blockIdx.x == 0 && item == 0 && lane == 0) p.trace[i * 24 + 8 + (warp - 2)] = clock64();      // every warp: TMEM released
+        if (TRACE && blockIdx.x == 0 && item == item0 && lane == 0) p.trace[i * 24 + 8 + (warp - 2)] = clock64();      // every warp: TMEM released
 
         // ---- diagonal block, in registers and in place: V^T[:, nt] = sum_{kt <= nt} rhs^T[:, kt] * Dinv^T[kt, nt]
         {
@@ -707,8 +737,12 @@ int ozaki_prepare_device(bopl_handle* h, cudaStream_t st) {
 namespace {
 template <int S>
 int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
-  const long long items = (long long)p.ntiles * h->m;
-  const int grid = (int)std::min<long long>(items, h->sms);
+  // CTA pairs (clusters of two sharing the factor's digit images) when there is enough work to keep every pair busy
+  const int npairs = (p.ntiles + 1) / 2 * h->m;
+  bool cl = h->oz_cluster != 0 && npairs >= h->sms / 2 && h->sms >= 2;
+  const long long items = cl ? 2LL * npairs : (long long)p.ntiles * h->m;
+  int grid = (int)std::min<long long>(items, h->sms);
+  if (cl) grid &= ~1;
   const int nb = h->n_pad / OB;
   int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)grid * nb * Oz<S>::VIMG);
   if (rc) return rc;
@@ -727,8 +761,9 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
   const size_t smem = oz_smem_bytes<S>(h->d);
   size_t& attr = h->oz_attr_smem[S - 6];
   if (smem > attr) {
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   p.trace = nullptr;
@@ -738,7 +773,7 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
     BOPL_CUDA(h, cudaMalloc((void**)&tb, tbytes));
     BOPL_CUDA(h, cudaMemsetAsync(tb, 0, tbytes, st));
     p.trace = tb;
-    posterior_ozaki_kernel<S, true><<<grid, ONT, smem, st>>>(p);
+    posterior_ozaki_kernel<S, true, false><<<(int)std::min<long long>((long long)p.ntiles * h->m, h->sms), ONT, smem, st>>>(p);
     BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
     std::vector<long long> host((size_t)nb * 24);
     BOPL_CUDA(h, cudaStreamSynchronize(st));
@@ -752,7 +787,23 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
     }
     return BOPL_OK;
   }
-  posterior_ozaki_kernel<S, false><<<grid, ONT, smem, st>>>(p);
+  if (cl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ONT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BOPL_CUDA(h, cudaLaunchKernelEx(&cfg, posterior_ozaki_kernel<S, false, true>, p));
+  } else {
+    posterior_ozaki_kernel<S, false, false><<<grid, ONT, smem, st>>>(p);
+  }
   BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
   return BOPL_OK;
 }

@@ -169,6 +169,22 @@ def test_blocked_kernels_against_reference_generated_golden(fname, kernel):
     assert np.argmax(a) == np.argmax(g["acq_sequential"])
 
 
+def test_int8_cluster_pairs_equal_single_ctas_bit_for_bit(monkeypatch):
+    """Large batches run as clusters of two CTAs sharing the factor's digit images by multicast (odd tile count: the last pair has a
+    tile past the end); the arithmetic per candidate is the same, so the results equal the single-CTA launch bit for bit."""
+    p = make_problem("S", n=300, N=149 * 128 - 37)          # 149 tiles x 3 attributes >= 74 pairs: the cluster launch
+    monkeypatch.setenv("BOPL_OZ_CLUSTER", "1")
+    g1 = gpu_model(p, gradients=False, posterior_kernel="int8")
+    mu1, v1 = g1.predict(p["Xc"])
+    monkeypatch.setenv("BOPL_OZ_CLUSTER", "0")
+    g0 = gpu_model(p, gradients=False, posterior_kernel="int8")
+    mu0, v0 = g0.predict(p["Xc"])
+    assert np.array_equal(mu1, mu0) and np.array_equal(v1, v0)
+    g64 = gpu_model(p, gradients=False)
+    mu_d, v_d = g64.predict(p["Xc"])
+    assert scaled_err(mu1, mu_d) < 1e-12 and rel_err(v1, v_d) < 1e-10
+
+
 def test_int8_posterior_many_block_rows():
     """n = 3000 (47 block rows of 64, front padding 8): more block rows, longer accumulation chains and larger accumulators than
     the benchmark shape; 6- and 7-digit kernels against the fp64 kernel and the oracle."""
