@@ -54,11 +54,7 @@ struct Oz {
 constexpr int NFRAG = 36;                    // lower-triangular 8x8 blocks of a 64x64 diagonal block
 constexpr int ONT = 320;                     // producer warp, MMA warp, eight compute warps
 constexpr int NCW = 8;
-#ifndef OZ_SWAP_ROLES
-constexpr int PROD_WARP = 0, MMA_WARP = 1;
-#else
-constexpr int PROD_WARP = 1, MMA_WARP = 0;
-#endif
+constexpr int PROD_WARP = 0, MMA_WARP = 1;   // lane 0 of each: bulk-copy producer, tcgen05.mma issuer; warps 2..9 compute
 
 struct OzParams {
   const GpDev* gps;
