@@ -796,7 +796,12 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    BOPL_CUDA(h, cudaLaunchKernelEx(&cfg, posterior_ozaki_kernel<S, false, true>, p));
+    const cudaError_t ce = cudaLaunchKernelEx(&cfg, posterior_ozaki_kernel<S, false, true>, p);
+    if (ce != cudaSuccess) {          // a device / driver that refuses this cluster shape: same kernel, one CTA per work item, from now on
+      (void)cudaGetLastError();
+      h->oz_cluster = 0;
+      return launch_oz<S>(h, p, st);
+    }
   } else {
     posterior_ozaki_kernel<S, false, false><<<grid, ONT, smem, st>>>(p);
   }
