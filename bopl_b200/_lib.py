@@ -10,14 +10,14 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
-SOURCES = ["api.cu", "posterior_trsm.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu", "posterior_ozaki.cu"]
+SOURCES = ["api.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu", "posterior_ozaki.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
-NVCC_FLAGS = (["-DOZ_SWAP_ROLES"] if os.environ.get("OZ_SWAP_ROLES") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0"]
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}
-POSTERIOR_KERNELS = {"fp64": 0, "int8": 6, "int8x7": 7}   # bopl_set_posterior_kernel
+POSTERIOR_KERNELS = {"fp64": 0, "int8": 6, "int8x7": 7}   # bopl_set_posterior_kernel; the library default is int8x7
 VAR_INCLUDE_NOISE = 1
 VAR_CLIP = 2
 ERR_NUMERIC = -5
@@ -45,9 +45,9 @@ def _source_hash():
     """Content hash of every source, header and flag the library is built from (mtimes do not survive a repo snapshot)."""
     import hashlib
     hh = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for path in [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, x)) for x in HEADERS]:
-        with open(path, "rb") as f:
-            hh.update(path.encode() + b"\0" + f.read())
+    for name in SOURCES + HEADERS:       # names relative to csrc/: the hash must not depend on where the repo is checked out
+        with open(os.path.normpath(os.path.join(CSRC, name)), "rb") as f:
+            hh.update(os.path.basename(name).encode() + b"\0" + f.read())
     return hh.hexdigest()
 
 

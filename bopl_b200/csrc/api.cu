@@ -153,18 +153,18 @@ int bopl_create(bopl_handle** out, int device) {
   bopl_handle* h = new bopl_handle();
   h->device = device;
   h->sms = prop.multiProcessorCount;
-  if (const char* v = getenv("BOPL_TRSM_VARIANT")) h->trsm_variant = atoi(v);
-  if (const char* v = getenv("BOPL_TRSM_STAGGER")) h->trsm_stagger = atoi(v);
   if (const char* v = getenv("BOPL_SMALL_PATH")) h->small_path = atoi(v);
-  if (const char* v = getenv("BOPL_OZAKI")) h->use_ozaki = atoi(v);
   if (const char* v = getenv("BOPL_OZ_CLUSTER")) h->oz_cluster = atoi(v);
-  if (const char* v = getenv("BOPL_OZAKI_DIGITS")) h->oz_digits = atoi(v) == 7 ? 7 : 6;
-  if (const char* v = getenv("BOPL_POSTERIOR")) {        // "fp64" (default), "int8" (6 digits), "int8x7"
+  if (const char* v = getenv("BOPL_POSTERIOR")) {        // "int8x7" (default), "int8" (6 digits), "fp64"
     const std::string k(v);
     if (k == "int8" || k == "int8x7") {
-      h->trsm_variant = 4;
       h->use_ozaki = 1;
       h->oz_digits = k == "int8" ? 6 : 7;
+    } else if (k == "fp64") {
+      h->use_ozaki = 0;
+    } else {
+      delete h;
+      return fail(nullptr, BOPL_ERR_INVALID, "BOPL_POSTERIOR must be int8x7, int8 or fp64");
     }
   }
   if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
@@ -189,7 +189,7 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->sm_slots, h->small_scratch, h->gh_dev, h->fit_ws, h->oz_scratch};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->small_scratch, h->gh_dev, h->fit_ws, h->oz_scratch};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -213,13 +213,11 @@ int bopl_set_posterior_kernel(bopl_handle* h, int kind) {
   if (!h) return fail(nullptr, BOPL_ERR_INVALID, "null handle");
   if (kind != BOPL_POSTERIOR_FP64 && kind != BOPL_POSTERIOR_INT8 && kind != BOPL_POSTERIOR_INT8_7)
     return fail(h, BOPL_ERR_INVALID, "unknown posterior kernel kind");
-  if (kind != BOPL_POSTERIOR_FP64 && h->has_model && (!h->has_oz || h->oz_digits != kind))
+  if (kind != BOPL_POSTERIOR_FP64 && h->has_model && ozaki_covers(h->d, h->n_pad) && (!h->has_oz || h->oz_digits != kind))
     return fail(h, BOPL_ERR_STATE, "the loaded model carries no digit images of that width: select the kernel before bopl_set_model / bopl_fit_model");
   if (kind == BOPL_POSTERIOR_FP64) {
-    if (h->trsm_variant == 4) h->trsm_variant = 3;
     h->use_ozaki = 0;
   } else {
-    h->trsm_variant = 4;
     h->use_ozaki = 1;
     h->oz_digits = kind;
   }
@@ -228,7 +226,7 @@ int bopl_set_posterior_kernel(bopl_handle* h, int kind) {
 
 int bopl_get_posterior_kernel(const bopl_handle* h) {
   if (!h) return -1;
-  return (h->trsm_variant == 4 && h->use_ozaki) ? h->oz_digits : BOPL_POSTERIOR_FP64;
+  return h->use_ozaki ? h->oz_digits : BOPL_POSTERIOR_FP64;
 }
 
 int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
@@ -298,7 +296,8 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     // int8 digit images for the INT8-tensor-pipe variant (posterior_ozaki.cu): from the un-negated factor
     std::vector<signed char> oz_img;
     std::vector<double> oz_scale, oz_d64;
-    if (h->use_ozaki) {
+    const bool oz = h->use_ozaki && ozaki_covers(d, n_pad);
+    if (oz) {
       ozaki_prepare(Lp.data(), n_pad, h->oz_digits, oz_img, oz_scale);
       const int nb64 = n_pad / 64;
       oz_d64.resize((size_t)nb64 * 64 * 64);
@@ -324,7 +323,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     pack_stage_blocks(Xs.data(), al.data(), n_pad, d, SBlk.data());
     signed char* pOzL = nullptr;
     double* pOzS = nullptr;
-    if (h->use_ozaki) {
+    if (oz) {
       std::vector<double> oz_stage;
       ozaki_pack_stage(oz_d64.data(), Xs.data(), al.data(), oz_scale.data(), n_pad, d, oz_stage);
       if ((rc = dev_upload(h, oz_img.data(), oz_img.size(), &pOzL)) || (rc = dev_upload(h, oz_stage.data(), oz_stage.size(), &pOzS))) {
@@ -375,7 +374,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   h->gp_dev = gd;
   h->has_winv = Winv_h != nullptr;
   h->has_linv = Linv_h != nullptr;
-  h->has_oz = h->use_ozaki != 0;
+  h->has_oz = h->use_ozaki != 0 && ozaki_covers(d, n_pad);
   h->has_model = true;
   h->F_valid = false;
   return BOPL_OK;

@@ -52,13 +52,8 @@ struct bopl_handle {
   int trsm_stages = 3;                 // BOPL_TRSM_STAGES=4: deeper pipeline when shared memory allows (measured no faster)
   double trsm_l2_keep_frac = 0.75;     // share of the L2 the posterior kernel may pin (factor + first panel block rows)
   int trsm_keep_blocks = -1;           // BOPL_TRSM_KEEP_BLOCKS: panel block rows per CTA kept in L2 (-1: from the budget)
-  int trsm_stagger = 1;                // BOPL_TRSM_STAGGER=0 disables the start offset of the second CTA per SM
-  int* sm_slots = nullptr;
-  size_t attr_smem[4] = {0, 0, 0, 0};
-  size_t attr_smem_t[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  int trsm_l2_hints = 1;               // BOPL_TRSM_L2_HINTS: 0 none, 1 eviction-priority hints on the L / V tile loads, 2 also on the V stores  // dynamic-smem attribute already set on THIS device, per posterior-kernel instantiation
-  int trsm_variant = 3;                // BOPL_TRSM_VARIANT: 3 candidate-owning warps, diagonal solve in registers (default);
-                                       // 1 row-owning 128x128 tiles, one CTA per SM; 2 row-owning 128x64 tiles, two CTAs per SM
+  size_t attr_smem_t[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // dynamic-smem attribute already set on THIS device, per posterior_trsm_t instantiation
+  int trsm_l2_hints = 1;               // BOPL_TRSM_L2_HINTS: 0 none, 1 eviction-priority hints on the L / V tile loads, 2 also on the V stores
   // model storage
   std::vector<void*> owned;            // every cudaMalloc'ed model buffer
   bopl::GpDev* gp_dev = nullptr;       // [m*H] device array, index j*H + h
@@ -81,10 +76,12 @@ struct bopl_handle {
   void* fit_ws = nullptr; size_t fit_ws_bytes = 0;   // workspace of bopl_log_marginal (factor, inverse, K^-1 of every instance)
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
   void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
-  int use_ozaki = 0;                   // BOPL_OZAKI=1: bopl_set_model also builds the int8 digit images (posterior_ozaki.cu)
+  // posterior kernel for batches above the small-batch limit (bopl_set_posterior_kernel / BOPL_POSTERIOR):
+  // use_ozaki = 1 (default): the update on the int8 tensor pipe (posterior_ozaki.cu), oz_digits per operand; 0: fp64 DMMA kernel
+  int use_ozaki = 1;
   bool has_oz = false;
   int oz_cluster = 1;                  // BOPL_OZ_CLUSTER=0 disables: CTA pairs sharing the factor's digit images by multicast (posterior_ozaki.cu)
-  int oz_digits = 6;                   // digits of the model's images (fixed at upload): 6 = 47 fractional bits, 7 = 55
+  int oz_digits = 7;                   // digits of the model's images (fixed at upload): 7 = 55 fractional bits (default), 6 = 47
   void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem[2] = {0, 0};
   size_t hsmall_cap = 0;
 };
@@ -139,8 +136,8 @@ int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, dou
                           cudaStream_t st);
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st);
-bool trsm_t_fits(int d);
 bool ozaki_available(const bopl_handle* h);
+bool ozaki_covers(int d, int n_pad);
 void ozaki_prepare(const double* Lp, int n_pad, int S, std::vector<signed char>& img, std::vector<double>& scale);
 int ozaki_prepare_device(bopl_handle* h, cudaStream_t st);
 void ozaki_pack_stage(const double* Dinv64, const double* Xs, const double* alpha, const double* scale, int n_pad, int d,

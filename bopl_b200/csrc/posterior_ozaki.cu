@@ -519,10 +519,9 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 
 }  // namespace
 
-bool ozaki_available(const bopl_handle* h) {
-  if (!h->has_oz || h->d > OZ_MAXD || h->n_pad > 16384) return false;
-  return true;
-}
+bool ozaki_covers(int d, int n_pad) { return d <= OZ_MAXD && n_pad <= 16384; }
+
+bool ozaki_available(const bopl_handle* h) { return h->has_oz && ozaki_covers(h->d, h->n_pad); }
 
 int ozaki_stage_doubles(int d) { return oz_sb_doubles(d); }
 
@@ -699,7 +698,7 @@ __global__ void oz_stage_kernel(const OzPrep* pp, int n_pad, int d) {
 // Builds OzL / OzStage of every GP in h->gp_host from its device-resident factor (call before the GpDev array is uploaded).
 int ozaki_prepare_device(bopl_handle* h, cudaStream_t st) {
   const int G = (int)h->gp_host.size(), n_pad = h->n_pad, d = h->d, nb = n_pad / OB, S = h->oz_digits;
-  if (h->d > OZ_MAXD || n_pad > 16384 || nb < 1) return BOPL_OK;   // the kernel does not cover these shapes: fp64 kernel only
+  if (!ozaki_covers(h->d, n_pad) || nb < 1) return BOPL_OK;   // the kernel does not cover these shapes: fp64 kernel only
   std::vector<OzPrep> prep(G);
   const size_t img_bytes = std::max<size_t>(16, (size_t)nb * (nb - 1) / 2 * S * OB * OB), stage_bytes = (size_t)nb * oz_sb_doubles(d) * 8;
   for (int gi = 0; gi < G; ++gi) {

@@ -1,8 +1,13 @@
-// posterior_trsm_t.cu — kernels (1)+(2) of the hot path, "candidate-owning" form (default since round 1, step 5).
-//
-// Same mathematics as posterior_trsm.cu (fused K* generation, left-looking blocked forward substitution on DMMA.8x8x4,
-// mean and variance epilogue; reference: posterior.py:299-320, gp.py:380-435, linalg.py:92-111), but the product is
-// formed TRANSPOSED, V^T[cand][row], and every warp owns 16 candidates x all 128 rows of the current block row:
+// posterior_trsm_t.cu — kernels (1)+(2) of the hot path in fp64 on the FP64 tensor pipe: per attribute, for a tile of 128 candidates,
+//   K* = K(X, Xc)                      (generated on the fly, never written to HBM)
+//   mu = K*^T alpha + ymean             (GPy posterior.py:299-305, gp.py:398-399)
+//   V  = L^{-1} K*                      (LAPACK dtrtrs in the reference: posterior.py:311, linalg.py:92-111)
+//   var = variance - colsum(V^2) (+noise, clip)   (posterior.py:312, gp.py:416-417, gpmodel.py:214)
+// as a LEFT-LOOKING BLOCKED forward substitution over 128-row blocks of L,
+//   V_ib = Dinv_ib * ( K*_ib + sum_{k<ib} (-L_ib,k) V_k ),   Dinv_ib = L_ib,ib^{-1} (precomputed per model update),
+// so that all flops are GEMM-shaped and run on DMMA.8x8x4 (mma.sync.m8n8k4.f64 — the only FP64 MMA shape sm_100a SASS has; tcgen05
+// has no f64 kind).  Persistent CTAs walk (attribute, candidate-tile) items, attribute-major so that all CTAs stream the same L
+// out of L2.  The product is formed TRANSPOSED, V^T[cand][row], and every warp owns 16 candidates x all 128 rows of the block row:
 //
 //   * main loop     acc[cand][row] += V^T[cand][k] * (-L)^T[k][row]     A = V tile [cand][16k], B = L tile [row][16k]
 //   * diagonal      V^T = rhs^T * Dinv^T.  The C fragment of an 8x8 tile holds (cand g, k = 2t, 2t+1): taken as the
@@ -342,7 +347,7 @@ int launch_t(bopl_handle* h, TParams& p, cudaStream_t st) {
     p.keep_tiles = (int)blocks * (TRSM_BM / TRSM_BK);
   }
   size_t smem = t_smem_bytes<STAGES>(h->d);
-  size_t& attr_smem = h->attr_smem_t[STAGES == 4 ? 0 : 1][HINTS];   // function attributes are per device: remember per handle
+  size_t& attr_smem = h->attr_smem_t[STAGES - 2][HINTS];   // function attributes are per device: remember per handle
   if (smem > attr_smem) {
     BOPL_CUDA(h, cudaFuncSetAttribute(posterior_trsm_t_kernel<STAGES, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
@@ -384,9 +389,6 @@ void pack_stage_blocks(const double* Xs /*n_pad*d*/, const double* alpha /*n_pad
   }
 }
 
-// The candidate-owning kernel keeps the staged inputs of two block rows in shared memory: it fits up to d = 20.
-bool trsm_t_fits(int d) { return t_smem_bytes<3>(d) + 256 <= 227 * 1024; }
-
 int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
                             cudaStream_t st) {
   if (N <= 0) return BOPL_OK;
@@ -403,10 +405,23 @@ int launch_posterior_trsm_t(bopl_handle* h, const double* Xc, int N, int hsel, d
   p.n_pad = h->n_pad;
   p.pad = h->pad;
   p.flags = flags;
+  // The kernel keeps the staged inputs of two block rows in shared memory: three pipeline stages fit up to d = 20, two up to d = 24 (MAX_D).
+  if (t_smem_bytes<3>(h->d) + 256 > 227 * 1024) return launch_t<2, 1>(h, p, st);
   if (h->trsm_stages == 4 && t_smem_bytes<4>(h->d) + 256 <= 227 * 1024) return launch_t<4, 0>(h, p, st);
   if (h->trsm_l2_hints == 2) return launch_t<3, 2>(h, p, st);
   if (h->trsm_l2_hints == 1) return launch_t<3, 1>(h, p, st);
   return launch_t<3, 0>(h, p, st);
+}
+
+// Posterior mean and variance of a batch: the kernel choice behind bopl_posterior / bopl_uei*.  N <= 32 with the inverse factor loaded:
+// matrix-vector path (gp_kernels.cu); otherwise the int8-tensor-pipe kernel (posterior_ozaki.cu) when it is selected and covers the
+// shape, else the fp64 DMMA kernel above.  All three are device kernels of this library; there is no other path.
+int launch_posterior_trsm(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, double* var, int flags,
+                          cudaStream_t st) {
+  if (N <= 0) return BOPL_OK;
+  if (use_small_path(h, N)) return launch_posterior_small(h, Xc, N, hsel, mean, var, flags, st);
+  if (h->use_ozaki && ozaki_available(h)) return launch_posterior_ozaki(h, Xc, N, hsel, mean, var, flags, st);
+  return launch_posterior_trsm_t(h, Xc, N, hsel, mean, var, flags, st);
 }
 
 }  // namespace bopl

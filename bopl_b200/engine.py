@@ -98,7 +98,8 @@ class Engine(object):
 
     # ------------------------------------------------------------------ model
     def set_posterior_kernel(self, kind):
-        """'fp64' (DMMA blocked solve, default), 'int8' (update on the int8 tensor pipe, 6-digit split) or 'int8x7' (7 digits).
+        """'int8x7' (update on the int8 tensor pipe, 7-digit = 55-bit exact split; default), 'fp64' (DMMA blocked solve) or
+        'int8' (6-digit split: opt-in reduced precision).
         Select before the model is uploaded / fitted: the digit images of the factor are built then (`bopl_set_posterior_kernel`)."""
         self._check(self.lib.bopl_set_posterior_kernel(self.h, _lib.POSTERIOR_KERNELS[kind]))
 

@@ -192,7 +192,7 @@ class MultiOutputGP(object):
         self.gradients = gradients
         self.fit_options = dict(fit_options or {})        # n_burnin, subsample_interval, step_size, leapfrog_steps, max_iters
         self.fit_on_device = fit_on_device                # False: LAPACK on the host + upload (bopl_set_model), as round 1 did
-        self.engine = Engine(device, posterior_kernel)    # None: the library default (fp64, or $BOPL_POSTERIOR); 'int8' / 'int8x7'
+        self.engine = Engine(device, posterior_kernel)    # None: the library default (int8x7, or $BOPL_POSTERIOR); 'fp64' / 'int8'
         self._hyps = None
         self._h = 0
         self.state = None

@@ -61,14 +61,18 @@ const char* bopl_build_info(void);
 
 /* Kernel behind bopl_posterior / bopl_uei* for batches above the small-batch limit (the reference has one NumPy path:
  * GPy/inference/latent_function_inference/posterior.py:299-320 — dtrtrs on the cached factor, then the column square-sum).
- *   BOPL_POSTERIOR_FP64   (default) fp64 DMMA.8x8x4 blocked triangular solve (posterior_trsm_t.cu);
- *   BOPL_POSTERIOR_INT8   the same solve with its n^2/2 update on the int8 tensor pipe (tcgen05.mma kind::i8, TMEM): both operands
- *                         split exactly into 6 base-256 digits (47 fractional bits against a power-of-two row scale), digit products
- *                         accumulated exactly in s32, recombined in fp64 (posterior_ozaki.cu).  Variance within ~2e-11 sigma^2 of the
- *                         fp64 kernel at n = 2000; 2.4x its speed.  Shapes it does not cover (d > 12, n > 16384) run the fp64 kernel.
- *   BOPL_POSTERIOR_INT8_7 7 digits (55 bits: every bit of an fp64 mantissa), 28 instead of 21 digit products.
- * Select BEFORE bopl_set_model / bopl_fit_model (the digit images of the factor are built at upload); switching back to FP64 is
- * always allowed.  Environment default: BOPL_POSTERIOR=fp64|int8|int8x7. */
+ *   BOPL_POSTERIOR_INT8_7 (default) blocked triangular solve whose n^2/2 update runs on the int8 tensor pipe (tcgen05.mma kind::i8,
+ *                         TMEM accumulators): both operands are split exactly into 7 base-256 digits (55 fractional bits against a
+ *                         power-of-two row scale — every bit of an fp64 mantissa), the 28 digit products with weight above 2^-56 are
+ *                         accumulated exactly in s32 and recombined in fp64; K*, the 64-row diagonal solves, mean and variance are fp64
+ *                         (posterior_ozaki.cu).  Passes the fp64 kernel's parity tolerances unchanged, including at candidates next
+ *                         to training points (tests/test_gpu_low_variance.py).  Shapes it does not cover (d > 12, n > 16384) run the
+ *                         fp64 kernel — a kernel choice inside this library, not a fallback path.
+ *   BOPL_POSTERIOR_FP64   fp64 DMMA.8x8x4 blocked triangular solve (posterior_trsm_t.cu), 0.95 of the cuBLAS DGEMM peak.
+ *   BOPL_POSTERIOR_INT8   opt-in REDUCED-PRECISION mode: 6 digits (47 fractional bits), 21 digit products.  Absolute error of the
+ *                         variance ~2e-11 sigma^2 at n = 2000, i.e. NOT within 1e-9 relative where the variance is below ~1e-2 sigma^2.
+ * Select BEFORE bopl_set_model / bopl_fit_model (the digit images of the factor are built at upload); switching to FP64 is
+ * always allowed.  Environment default: BOPL_POSTERIOR=int8x7|fp64|int8. */
 #define BOPL_POSTERIOR_FP64 0
 #define BOPL_POSTERIOR_INT8 6
 #define BOPL_POSTERIOR_INT8_7 7

@@ -51,7 +51,7 @@ def test_int8_posterior_config_S_plain_relative(kernel):
     the int8 kernels against the fp64 kernel itself: 1e-10 (6 digits) / 1e-12 (7 digits) relative."""
     p = make_problem("S", N=4096)
     om = oracle_model(p)
-    gm, g64 = gpu_model(p, gradients=False, posterior_kernel=kernel), gpu_model(p, gradients=False)
+    gm, g64 = gpu_model(p, gradients=False, posterior_kernel=kernel), gpu_model(p, gradients=False, posterior_kernel="fp64")
     mu_o, v_o = om.predict(p["Xc"])
     mu_g, v_g = gm.predict(p["Xc"])
     mu_d, v_d = g64.predict(p["Xc"])
@@ -138,7 +138,7 @@ def test_int8_uei_values_and_argmax():
     fp64 kernel's."""
     p = make_problem("S", n=600, N=5000)
     om = oracle_model(p)
-    gm, g64 = gpu_model(p, gradients=False, posterior_kernel="int8"), gpu_model(p, gradients=False)
+    gm, g64 = gpu_model(p, gradients=False, posterior_kernel="int8"), gpu_model(p, gradients=False, posterior_kernel="fp64")
     a8 = gpu_acquisition(p, gm)._compute_acq(p["Xc"])[:, 0]
     a64 = gpu_acquisition(p, g64)._compute_acq(p["Xc"])[:, 0]
     marg = oacq.uei_marginal_vec(om, p["utility"], p["theta"], p["Z"], p["Xc"], 1)
@@ -180,7 +180,7 @@ def test_int8_cluster_pairs_equal_single_ctas_bit_for_bit(monkeypatch):
     g0 = gpu_model(p, gradients=False, posterior_kernel="int8")
     mu0, v0 = g0.predict(p["Xc"])
     assert np.array_equal(mu1, mu0) and np.array_equal(v1, v0)
-    g64 = gpu_model(p, gradients=False)
+    g64 = gpu_model(p, gradients=False, posterior_kernel="fp64")
     mu_d, v_d = g64.predict(p["Xc"])
     assert scaled_err(mu1, mu_d) < 1e-12 and rel_err(v1, v_d) < 1e-10
 
@@ -191,7 +191,7 @@ def test_int8_posterior_many_block_rows():
     p = make_problem("S", n=3000, N=400)
     om = oracle_model(p)
     mu_o, v_o = om.predict(p["Xc"])
-    g64 = gpu_model(p, gradients=False)
+    g64 = gpu_model(p, gradients=False, posterior_kernel="fp64")
     mu_d, v_d = g64.predict(p["Xc"])
     for kernel, tol in (("int8", 2e-10), ("int8x7", 2e-12)):
         gm = gpu_model(p, gradients=False, posterior_kernel=kernel)
@@ -204,9 +204,10 @@ def test_int8_posterior_many_block_rows():
 def test_int8_kernel_selection_rules():
     from bopl_b200._lib import BoplError
     p = make_problem("portfolio1", n=80, N=50)
-    gm = gpu_model(p)                                   # fp64 model: no digit images
+    gm = gpu_model(p, posterior_kernel="fp64")          # fp64 model: no digit images
     with pytest.raises(BoplError):
         gm.engine.set_posterior_kernel("int8")
+    assert gpu_model(p).engine.posterior_kernel == "int8x7"     # the library default
     g8 = gpu_model(p, posterior_kernel="int8")
     with pytest.raises(BoplError):
         g8.engine.set_posterior_kernel("int8x7")        # images of the other width
@@ -223,15 +224,17 @@ def test_int8_kernel_selection_rules():
     X, Xc = rs.uniform(size=(n, d)), rs.uniform(size=(70, d))
     Y = np.stack([np.sin(X @ rs.normal(size=d)) for _ in range(m)])
     st = state_from_hyperparameters(X, Y, ["Mat52"] * m, np.ones((m, 1)), np.full((m, 1, d), 3.0), np.full((m, 1), 1e-4))
-    a, b = MultiOutputGP.from_state(st, posterior_kernel="int8"), MultiOutputGP.from_state(st)
+    a, b = MultiOutputGP.from_state(st, posterior_kernel="int8"), MultiOutputGP.from_state(st, posterior_kernel="fp64")
     assert np.array_equal(a.predict(Xc)[1], b.predict(Xc)[1])
 
 
-def test_int8_full_size_config_S():
-    """Config S at BASELINE.json's full size through the reference-facing call with the int8 kernel: finite non-negative scores,
+@pytest.mark.parametrize("kernel", ["int8"])
+def test_int8_full_size_config_S(kernel):
+    """Config S at BASELINE.json's full size through the reference-facing call with the 6-digit kernel (the 7-digit default runs
+    tests/test_gpu_parity.py::test_full_size_config_S_properties_and_subset_parity): finite non-negative scores,
     anchors = stable argsort, bitwise sub-batch reproducibility, and the same top-20 anchors as the fp64 kernel."""
     p = make_problem("S")
-    gm = gpu_model(p, gradients=False, posterior_kernel="int8")
+    gm = gpu_model(p, gradients=False, posterior_kernel=kernel)
     acq = gpu_acquisition(p, gm)
     val, idx, a = acq.top_candidates(p["Xc"], 20, want_acq=True)
     assert a.shape == (2 ** 20,) and np.all(np.isfinite(a)) and np.all(a >= 0.0)
@@ -239,7 +242,7 @@ def test_int8_full_size_config_S():
     assert np.array_equal(idx, want) and np.array_equal(val, a[want])
     sl = slice(300000, 300000 + 70001)
     assert np.array_equal(acq._compute_acq(p["Xc"][sl])[:, 0], a[sl])
-    g64 = gpu_model(p, gradients=False)
+    g64 = gpu_model(p, gradients=False, posterior_kernel="fp64")
     val64, idx64, a64 = gpu_acquisition(p, g64).top_candidates(p["Xc"], 20, want_acq=True)
     assert np.array_equal(idx, idx64)
     assert scaled_err(a, a64) < 1e-10

@@ -91,10 +91,22 @@ def check_close(got, want, what, rtol=RTOL):
 
 
 # ------------------------------------------------------------------------------------------------- posterior
+# The two full-precision posterior kernels — the library default (int8x7: the solve's update as exact 55-bit digit products on the
+# int8 tensor pipe) and the fp64 DMMA kernel — run the SAME tests under the SAME tolerances.  Every other test in this file uses
+# the library default.
+FULL_PRECISION_KERNELS = ["int8x7", "fp64"]
+
+
+def test_library_default_posterior_kernel_is_the_full_precision_int8_split():
+    p = make_problem("dtlz1a_linear")
+    assert gpu_model(p).engine.posterior_kernel == "int8x7"
+
+
+@pytest.mark.parametrize("kernel", FULL_PRECISION_KERNELS)
 @pytest.mark.parametrize("name", CONFIGS)
-def test_posterior_named_configs(name):
+def test_posterior_named_configs(name, kernel):
     p = make_problem(name)
-    om, gm = oracle_model(p), gpu_model(p)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
     X = p["Xc"]
     mu_o, v_o = om.predict(X)
     mu_g, v_g = gm.predict(X)
@@ -111,10 +123,11 @@ def test_posterior_named_configs(name):
     check_close(gm.posterior_mean_at_evaluated_points(), om.posterior_mean_at_evaluated_points(), name + " F")
 
 
-def test_posterior_config_S_plain_relative():
+@pytest.mark.parametrize("kernel", FULL_PRECISION_KERNELS)
+def test_posterior_config_S_plain_relative(kernel):
     """Benchmark shape (n=2000, m=3, d=10), first 4096 candidates: plain 1e-9 relative on mean AND variance."""
     p = make_problem("S", N=4096)
-    om, gm = oracle_model(p), gpu_model(p, gradients=False)
+    om, gm = oracle_model(p), gpu_model(p, gradients=False, posterior_kernel=kernel)
     mu_o, v_o = om.predict(p["Xc"])
     mu_g, v_g = gm.predict(p["Xc"])
     assert rel_err(v_g, v_o) < RTOL, rel_err(v_g, v_o)
@@ -139,11 +152,13 @@ def test_cross_cov_kernels(kind):
     assert np.all(np.abs(v_g - v_o) <= RTOL * np.abs(v_o) + 64 * floor + 1e-300)
 
 
-@pytest.mark.parametrize("n,N", [(1, 1), (5, 3), (127, 129), (128, 128), (129, 1), (300, 257), (513, 1000)])
-def test_posterior_ragged_shapes(n, N):
-    """Training sets that are not multiples of the 128-row block, candidate counts that are not multiples of the tile."""
+@pytest.mark.parametrize("kernel", FULL_PRECISION_KERNELS)
+@pytest.mark.parametrize("n,N", [(1, 1), (5, 3), (63, 129), (64, 128), (65, 257), (127, 129), (128, 128), (129, 1), (129, 33), (300, 257), (513, 1000)])
+def test_posterior_ragged_shapes(n, N, kernel):
+    """Training sets that are not multiples of the 64- / 128-row block (front padding), one block row only, candidate counts that are
+    not multiples of the 128-candidate tile (batches of <= 32 take the matrix-vector path whatever the kernel)."""
     p = make_problem("portfolio1", n=n, N=N)
-    om, gm = oracle_model(p), gpu_model(p)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
     mu_o, v_o = om.predict(p["Xc"])
     mu_g, v_g = gm.predict(p["Xc"])
     check_close(mu_g, mu_o, "mean n=%d N=%d" % (n, N))
@@ -161,10 +176,11 @@ def test_empty_batch_and_1d_input():
     assert np.array_equal(mu1, mu2) and np.array_equal(v1, v2)
 
 
-def test_variance_clip_and_noise_at_training_points():
+@pytest.mark.parametrize("kernel", FULL_PRECISION_KERNELS)
+def test_variance_clip_and_noise_at_training_points(kernel):
     """At the evaluated points the raw variance is ~0: the 1e-10 clip (gpmodel.py:214) and the noise term apply."""
     p = make_problem("dtlz2a_quad")
-    om, gm = oracle_model(p), gpu_model(p)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
     _, v_g = gm.predict_noiseless(p["X"])
     assert np.all(v_g >= 1e-10)
     _, v_n = gm.predict(p["X"])
@@ -173,9 +189,10 @@ def test_variance_clip_and_noise_at_training_points():
     check_close(mu_g, om.posterior_mean(p["X"]), "mean at train")
 
 
-def test_hyper_samples_select():
+@pytest.mark.parametrize("kernel", FULL_PRECISION_KERNELS)
+def test_hyper_samples_select(kernel):
     p = make_problem("dtlz1a_linear", H=3)
-    om, gm = oracle_model(p), gpu_model(p)
+    om, gm = oracle_model(p), gpu_model(p, posterior_kernel=kernel)
     for h in range(3):
         om.set_hyperparameters(h)
         gm.set_hyperparameters(h)
