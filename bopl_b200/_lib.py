@@ -10,10 +10,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbopl_b200.so")
-SOURCES = ["api.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu", "posterior_ozaki.cu"]
+SOURCES = ["api.cu", "posterior_trsm_t.cu", "gp_kernels.cu", "uei_kernels.cu", "topk.cu", "fit_kernels.cu", "path_kernels.cu", "posterior_ozaki.cu", "collective.cu", "probes.cu"]
 HEADERS = ["common.cuh", "pipeline.cuh", os.path.join("..", "..", "include", "bopl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--threads", "0", "-ldl"]
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}
@@ -27,7 +27,9 @@ SYMBOLS = ["bopl_create", "bopl_destroy", "bopl_last_error", "bopl_device_sms", 
            "bopl_cross_cov", "bopl_posterior", "bopl_posterior_mean", "bopl_train_mean", "bopl_posterior_grad",
            "bopl_incumbent", "bopl_uei_mc", "bopl_uei", "bopl_uei_grad", "bopl_uei_affine", "bopl_uei_constrained", "bopl_expected_utility", "bopl_topk",
            "bopl_uei_host", "bopl_uei_grad_host", "bopl_launch_count", "bopl_fit_model", "bopl_log_marginal",
-           "bopl_get_factor", "bopl_set_posterior_kernel", "bopl_get_posterior_kernel", "bopl_path_begin", "bopl_path_eval_host", "bopl_path_length", "bopl_path_end"]
+           "bopl_get_factor", "bopl_set_posterior_kernel", "bopl_get_posterior_kernel", "bopl_path_begin", "bopl_path_eval_host", "bopl_path_length", "bopl_path_end",
+           "bopl_nccl_unique_id", "bopl_nccl_comm_init", "bopl_nccl_comm_destroy", "bopl_topk_allgather", "bopl_topk_allgather_host",
+           "bopl_topk_pack", "bopl_topk_merge", "bopl_probe_int8_peak", "bopl_fit_info"]
 
 
 class BoplError(RuntimeError):
@@ -101,6 +103,7 @@ def load():
     lib.bopl_build_info.restype = ctypes.c_char_p
     lib.bopl_set_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.bopl_fit_model.argtypes = [vp, c_int, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, c_int, c_int, dp]
+    lib.bopl_fit_info.argtypes = [vp, c_int, ip]
     lib.bopl_log_marginal.argtypes = [vp, c_int, c_int, c_int, ip, dp, dp, dp, dp, dp, dp, dp, ip]
     lib.bopl_get_factor.argtypes = [vp, c_int, c_int, dp, dp, dp, dp]
     lib.bopl_cross_cov.argtypes = [vp, dp, c_int, c_int, c_int, dp, vp]
@@ -124,6 +127,14 @@ def load():
     lib.bopl_path_length.argtypes = [vp]
     lib.bopl_path_end.argtypes = [vp]
     lib.bopl_launch_count.argtypes = [vp]
+    lib.bopl_probe_int8_peak.argtypes = [vp, c_dbl, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]
+    lib.bopl_nccl_unique_id.argtypes = [vp]
+    lib.bopl_nccl_comm_init.argtypes = [vp, c_int, c_int, vp, ctypes.POINTER(vp)]
+    lib.bopl_nccl_comm_destroy.argtypes = [vp]
+    lib.bopl_topk_allgather.argtypes = [vp, vp, dp, llp, c_int, dp, c_ll, c_int, dp, llp, dp, vp]
+    lib.bopl_topk_allgather_host.argtypes = [vp, vp, dp, llp, c_int, dp, c_int, dp, llp, dp]
+    lib.bopl_topk_pack.argtypes = [vp, dp, llp, c_int, dp, c_ll, c_int, dp, vp]
+    lib.bopl_topk_merge.argtypes = [vp, dp, c_int, c_int, dp, llp, dp, vp]
     lib.bopl_set_posterior_kernel.argtypes = [vp, c_int]
     lib.bopl_get_posterior_kernel.argtypes = [vp]
     lib.bopl_launch_count.restype = c_ll

@@ -47,6 +47,9 @@ void free_model(bopl_handle* h) {
 
 namespace {
 
+// Synchronous upload from (pageable) host memory on the legacy stream.  cudaMemcpy may return once the data sits in the driver's staging
+// buffer, and the library's own streams are non-blocking (no implicit ordering with the legacy stream): every caller finishes its
+// uploads with uploads_done() before a kernel on s_compute / s_copy / the caller's stream may read them.
 template <typename T>
 int dev_upload(bopl_handle* h, const T* src, size_t count, T** out) {
   void* p = nullptr;
@@ -54,6 +57,11 @@ int dev_upload(bopl_handle* h, const T* src, size_t count, T** out) {
   h->owned.push_back(p);
   if (count) BOPL_CUDA(h, cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
   *out = (T*)p;
+  return BOPL_OK;
+}
+
+int uploads_done(bopl_handle* h) {
+  BOPL_CUDA(h, cudaDeviceSynchronize());
   return BOPL_OK;
 }
 
@@ -179,6 +187,7 @@ int bopl_create(bopl_handle** out, int device) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming);
   *out = h;
   return BOPL_OK;
 }
@@ -189,13 +198,14 @@ void bopl_destroy(bopl_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   void* bufs[] = {h->trsm_scratch, h->mean_s, h->var_s, h->dmean_s, h->dvar_s, h->grad_scratch, h->acq_s, h->F_s,
-                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->small_scratch, h->gh_dev, h->fit_ws, h->oz_scratch};
+                  h->topk_val_s, h->topk_idx_s, h->hx_dev, h->hacq_dev, h->hsmall_dev, h->small_scratch, h->gh_dev, h->fit_ws, h->oz_scratch, h->coll_s};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   delete h;
@@ -371,6 +381,10 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     free_model(h);
     return rc;
   }
+  if ((rc = uploads_done(h))) {
+    free_model(h);
+    return rc;
+  }
   h->gp_dev = gd;
   h->has_winv = Winv_h != nullptr;
   h->has_linv = Linv_h != nullptr;
@@ -383,6 +397,7 @@ int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
 int bopl_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, double* K, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || hsel < 0 || hsel >= h->H || j < 0 || j >= h->m) return fail(h, BOPL_ERR_INVALID, "bad N / hsel / j");
   if (N && (!Xc || !K)) return fail(h, BOPL_ERR_INVALID, "null buffer");
   return launch_cross_cov(h, Xc, N, hsel, j, K, (cudaStream_t)stream);
@@ -392,6 +407,7 @@ int bopl_posterior(bopl_handle* h, const double* Xc, int N, int hsel, double* me
                    void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
   if (N && !Xc) return fail(h, BOPL_ERR_INVALID, "null candidates");
   if (!var) return mean ? launch_posterior_mean(h, Xc, N, hsel, mean, (cudaStream_t)stream) : BOPL_OK;
@@ -401,6 +417,7 @@ int bopl_posterior(bopl_handle* h, const double* Xc, int N, int hsel, double* me
 int bopl_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, double* mean, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
   if (N && (!Xc || !mean)) return fail(h, BOPL_ERR_INVALID, "null buffer");
   return launch_posterior_mean(h, Xc, N, hsel, mean, (cudaStream_t)stream);
@@ -409,6 +426,7 @@ int bopl_posterior_mean(bopl_handle* h, const double* Xc, int N, int hsel, doubl
 int bopl_train_mean(bopl_handle* h, double* F, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (!F) return fail(h, BOPL_ERR_INVALID, "null buffer");
   return train_mean(h, F, (cudaStream_t)stream);
 }
@@ -417,6 +435,7 @@ int bopl_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, doubl
                         void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || hsel < 0 || hsel >= h->H) return fail(h, BOPL_ERR_INVALID, "bad N / hsel");
   if (N && !Xc) return fail(h, BOPL_ERR_INVALID, "null candidates");
   if (dvar && !h->has_winv) return fail(h, BOPL_ERR_STATE, "variance gradient needs Winv (bopl_set_model was given NULL)");
@@ -426,6 +445,7 @@ int bopl_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, doubl
 int bopl_incumbent(bopl_handle* h, int util_kind, const double* theta, int Lt, int p, double* best, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (!theta || !best) return fail(h, BOPL_ERR_INVALID, "null buffer");
@@ -449,6 +469,7 @@ int bopl_uei_mc(bopl_handle* h, const double* mean, const double* var, int N, co
                 double scale, int accumulate, double* acq, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (util_kind == BOPL_UTIL_CONSTRAINED) return fail(h, BOPL_ERR_INVALID, "the constrained utility has no MC kernel: use bopl_uei_constrained");
@@ -463,6 +484,7 @@ int bopl_uei(bopl_handle* h, const double* Xc, int N, const double* Z, int nw, i
              void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
@@ -476,6 +498,7 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
                   double* acq, double* dacq, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
@@ -500,6 +523,7 @@ int bopl_uei_grad_host(bopl_handle* h, const double* Xc_h, int N, const double* 
                        double* acq_h, double* dacq_h) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, h->s_compute);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH");
@@ -543,6 +567,7 @@ int bopl_expected_utility(bopl_handle* h, const double* Xc, int N, const double*
                           void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (util_kind == BOPL_UTIL_CONSTRAINED) return fail(h, BOPL_ERR_INVALID, "the constrained utility has no MC kernel");
@@ -573,6 +598,7 @@ int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta
                     const double* best, int nH, double* acq, double* dacq, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || Lt <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / Lt / nH");
   if (N == 0) return BOPL_OK;
   if (!Xc || !theta || !wts || !best || !acq) return fail(h, BOPL_ERR_INVALID, "null buffer");
@@ -596,6 +622,7 @@ int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* 
                          const double* best, int nH, double* acq, double* dacq, void* stream) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || Lt <= 0 || nH <= 0 || nH > h->H) return fail(h, BOPL_ERR_INVALID, "bad N / Lt / nH");
   if (h->m < 2) return fail(h, BOPL_ERR_INVALID, "constrained EI needs at least one constraint attribute (m >= 2)");
   if (N == 0) return BOPL_OK;
@@ -619,6 +646,7 @@ int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* 
 int bopl_topk(bopl_handle* h, const double* acq, int N, int k, long long index_offset, double* val,
               long long* idx, void* stream) {
   BOPL_CHECK_HANDLE(h);
+  StreamOrder order_guard(h, (cudaStream_t)stream);
   if (N < 0 || k < 0) return fail(h, BOPL_ERR_INVALID, "bad N / k");
   if (k == 0) return BOPL_OK;
   if (!acq || !val || !idx) return fail(h, BOPL_ERR_INVALID, "null buffer");
@@ -630,6 +658,7 @@ int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, 
                   double* acq_h, int k, long long index_offset, double* topk_val_h, long long* topk_idx_h) {
   BOPL_CHECK_HANDLE(h);
   BOPL_NEED_MODEL(h);
+  StreamOrder order_guard(h, h->s_compute);
   int rc = check_utility(h, util_kind, Lt, p);
   if (rc) return rc;
   if (N < 0 || nw <= 0 || nH <= 0 || nH > h->H || k < 0) return fail(h, BOPL_ERR_INVALID, "bad N / nw / nH / k");
@@ -774,7 +803,7 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   }
   char* fits_dev;
   const double t2 = now();
-  if ((rc = dev_upload(h, fits.data(), fits.size(), &fits_dev)) ||
+  if ((rc = dev_upload(h, fits.data(), fits.size(), &fits_dev)) || (rc = uploads_done(h)) ||
       (rc = fit_factorize(h, fits_dev, G, h->X_dev, n, d, inverse, want_winv != 0, want_linv != 0, h->s_compute))) {
     cleanup();
     free_model(h);
@@ -794,6 +823,7 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   std::vector<double> logdiag((size_t)G * nblk);
   BOPL_CUDA(h, cudaMemcpy(info.data(), info_dev, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
   BOPL_CUDA(h, cudaMemcpy(logdiag.data(), logdiag_dev, logdiag.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  h->fit_info = info;
   for (int g = 0; g < G; ++g)
     if (info[g]) {
       free_model(h);
@@ -820,12 +850,22 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
     free_model(h);
     return rc;
   }
+  if ((rc = uploads_done(h))) {
+    free_model(h);
+    return rc;
+  }
   h->gp_dev = gd;
   h->has_winv = want_winv != 0;
   h->has_linv = want_linv != 0;
   h->has_oz = oz_ok;
   h->has_model = true;
   h->F_valid = false;
+  return BOPL_OK;
+}
+
+int bopl_fit_info(const bopl_handle* h, int count, int* info_h) {
+  if (!h || !info_h || count < 0) return fail(nullptr, BOPL_ERR_INVALID, "null handle / buffer");
+  for (int g = 0; g < count; ++g) info_h[g] = g < (int)h->fit_info.size() ? h->fit_info[g] : 0;
   return BOPL_OK;
 }
 

@@ -58,6 +58,7 @@ struct bopl_handle {
   std::vector<void*> owned;            // every cudaMalloc'ed model buffer
   bopl::GpDev* gp_dev = nullptr;       // [m*H] device array, index j*H + h
   std::vector<bopl::GpDev> gp_host;    // host mirror
+  std::vector<int> fit_info;           // per (attribute, hyper-sample) instance of the last bopl_fit_model: 0, or 1 + the failed pivot
   double* X_dev = nullptr;             // [n*d] unscaled training inputs
   // scratch
   double* trsm_scratch = nullptr; size_t trsm_scratch_bytes = 0;   // per-CTA V panels
@@ -70,11 +71,13 @@ struct bopl_handle {
   // host-path staging
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_order = nullptr; cudaStream_t order_stream = nullptr; bool order_valid = false;   // cross-stream ordering of the scratch (api.cu)
   double* hx_dev = nullptr; size_t hx_cap = 0;       // [2][chunk*d] candidate double buffer
   double* hacq_dev = nullptr; size_t hacq_cap = 0;   // [N]
   double* gh_dev = nullptr; size_t gh_cap = 0;       // staging of the host-buffer value+gradient call
   void* fit_ws = nullptr; size_t fit_ws_bytes = 0;   // workspace of bopl_log_marginal (factor, inverse, K^-1 of every instance)
   double* hsmall_dev = nullptr;        // Z, theta, wts, best staging
+  double* coll_s = nullptr; size_t coll_bytes = 0;   // send / receive records of bopl_topk_allgather (collective.cu)
   void* path = nullptr;                // Thompson sample path in progress (path_kernels.cu)
   // posterior kernel for batches above the small-batch limit (bopl_set_posterior_kernel / BOPL_POSTERIOR):
   // use_ozaki = 1 (default): the update on the int8 tensor pipe (posterior_ozaki.cu), oz_digits per operand; 0: fp64 DMMA kernel
@@ -117,6 +120,23 @@ int fail(bopl_handle* h, int code, const std::string& msg);
   do {                                                                                            \
     if (!(h)->has_model) return bopl::fail((h), BOPL_ERR_STATE, "bopl_set_model has not been called"); \
   } while (0)
+
+// The handle's scratch buffers (mean / variance, gradients, solved panels, F, top-k levels) are shared by every entry point.  Calls on
+// ONE stream are ordered by the stream; when consecutive calls on a handle use DIFFERENT streams (a caller's torch stream, then a
+// host-buffer entry point on the library's own s_compute) the later stream first waits for an event recorded behind the earlier call.
+struct StreamOrder {
+  bopl_handle* h;
+  cudaStream_t st;
+  StreamOrder(bopl_handle* h_, cudaStream_t st_) : h(h_), st(st_) {
+    if (h->order_valid && h->order_stream != st) cudaStreamWaitEvent(st, h->ev_order, 0);
+  }
+  ~StreamOrder() {
+    if (cudaEventRecord(h->ev_order, st) == cudaSuccess) {
+      h->order_stream = st;
+      h->order_valid = true;
+    }
+  }
+};
 
 int ensure_bytes(bopl_handle* h, void** p, size_t* cap, size_t bytes);
 void free_model(bopl_handle* h);
@@ -219,6 +239,26 @@ __device__ const double EXP2_64TH[64] = {
 __device__ __forceinline__ double exp_nonpos(double x) {
   x = fmax(x, -700.0);
   const double magic = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest integer in the low word
+  double kd = fma(x, 0x1.71547652b82fep+6, magic);
+  const int n = __double2loint(kd);
+  kd -= magic;
+  double r = fma(kd, -0x1.62e42fee00000p-7, x);
+  r = fma(kd, -0x1.a39ef35793c76p-39, r);
+  const double t = __ldg(&EXP2_64TH[n & 63]);
+  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  const double em = fma(q, r * r, r);
+  const double p = fma(t, em, t);
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+}
+
+// exp(x) for any finite x, same table-driven evaluation (clamped at +-700 instead of producing 0 / inf): the exponential utility of
+// the MC kernel (experiments/test_vlmop3_exp.py:41-52) evaluates it m n_w L times per candidate — 6.4e9 per launch at the benchmark
+// shape, 14 ms with libm's exp against ~4 ms with this one (10 fp64 operations, <= 1 ulp).
+__device__ __forceinline__ double exp_any(double x) {
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double magic = 6755399441055744.0;
   double kd = fma(x, 0x1.71547652b82fep+6, magic);
   const int n = __double2loint(kd);
   kd -= magic;

@@ -345,6 +345,7 @@ int bopl_path_eval_host(bopl_handle* h, const double* x_h, const double* z_h, do
   if (!ps) return fail(h, BOPL_ERR_STATE, "bopl_path_begin has not been called");
   if (!x_h || !z_h || !y_h) return fail(h, BOPL_ERR_INVALID, "null buffer");
   cudaStream_t st = h->s_compute;
+  StreamOrder order_guard(h, st);
   int rc;
   if (ps->t == ps->cap && (rc = reserve(h, ps, 2 * ps->cap, st))) return rc;
   const int m = ps->m, d = ps->d, n = ps->n, t = ps->t;

@@ -34,7 +34,7 @@ __device__ __forceinline__ double utility_value(const double* a, const double* t
     } else {
       const double t0 = th[0];
 #pragma unroll
-      for (int j = 0; j < M; ++j) u += 1.0 - exp(-t0 * a[j]);
+      for (int j = 0; j < M; ++j) u += 1.0 - exp_any(-t0 * a[j]);
       u = u / t0 / (double)M;
     }
     return u;
@@ -61,7 +61,7 @@ __device__ __forceinline__ double utility_value(const double* a, const double* t
     const double t0 = th[0];
 #pragma unroll
     for (int j = 0; j < MAX_M; ++j)
-      if (j < m) u += 1.0 - exp(-t0 * a[j]);
+      if (j < m) u += 1.0 - exp_any(-t0 * a[j]);
     u = u / t0 / (double)m;
   }
   return u;
@@ -72,7 +72,7 @@ template <int KIND>
 __device__ __forceinline__ double utility_grad(double aj, const double* th, int m, int j) {
   if (KIND == BOPL_UTIL_LINEAR) return th[j];
   if (KIND == BOPL_UTIL_QUADRATIC) return -2.0 * (aj - th[j]);
-  return exp(-th[0] * aj) / (double)m;
+  return exp_any(-th[0] * aj) / (double)m;
 }
 
 struct McParams {

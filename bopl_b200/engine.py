@@ -142,17 +142,23 @@ class Engine(object):
         p = lambda a: ctypes.c_void_p(a.ctypes.data)
         logdet = np.empty((m, H))
         jitter = np.zeros((m, H))
-        tries = 0
+        tries = np.zeros((m, H), dtype=np.int64)
+        info = np.zeros((m, H), dtype=np.int32)
         while True:
             rc = self.lib.bopl_fit_model(self.h, n, d, m, H, p(kind_ids), p(X), p(Ym), p(lengthscale), p(variance), p(noise),
                                          p(jitter), int(bool(want_winv)), int(bool(want_linv)), p(logdet))
-            if rc != _lib.ERR_NUMERIC or tries >= max_tries:
+            if rc != _lib.ERR_NUMERIC:
                 break
-            # jitchol: jitter = mean(diag) * 1e-6, then x10 per retry (applied to every instance: the failed one is named
-            # in the message only)
-            base = (variance + noise + 1e-8) * 1e-6
-            jitter = base * (10.0 ** tries)
-            tries += 1
+            # jitchol (GPy/util/linalg.py:53-78) PER MATRIX: only the instances whose factorisation failed get jitter —
+            # mean(diag) * 1e-6, then x10 per retry, at most max_tries times; the healthy instances keep their factors unchanged
+            self._check(self.lib.bopl_fit_info(self.h, m * H, p(info)))
+            failed = info != 0
+            if not failed.any() or np.any(tries[failed] >= max_tries):
+                break
+            jitter[failed] = ((variance + noise + 1e-8) * 1e-6)[failed] * (10.0 ** tries[failed])
+            tries[failed] += 1
+        if rc != 0:
+            self.state = None                   # the device holds no model now (bopl_fit_model frees it first): fail clearly later
         self._check(rc)
         state = GPState(kinds, X, lengthscale, variance, noise, np.repeat(Ym.mean(axis=1)[:, None], H, axis=1), None, None, Y=Ym)
         state.on_device = True

@@ -123,8 +123,15 @@ class GPObjective(object):
         # Gamma(a, b) log prior on every positive hyper-parameter
         lp = np.sum(_GAMMA_A * np.log(_GAMMA_B) - gammaln(_GAMMA_A) + (_GAMMA_A - 1.0) * np.log(th) - _GAMMA_B * th)
         g_th = g_th + ((_GAMMA_A - 1.0) / th - _GAMMA_B)
+        # ... and, as GPy does for every priored parameter behind a transformation (core/parameterization/priorizable.py:57-65,76-81),
+        # the log-Jacobian of the Logexp transform: paramz 0.9.5 Logexp.log_jacobian(theta) = log(exp(theta) - 1) - theta
+        # = log(1 - exp(-theta)), gradient 1 / (exp(theta) - 1).  Without it MAP and HMC target a different (and, as theta -> 0,
+        # improper) density.
+        with np.errstate(over="ignore"):
+            lj = np.sum(np.log(-np.expm1(-th)))
+            g_th = g_th + 1.0 / np.expm1(th)
         dth_dx = 1.0 / (1.0 + np.exp(-x))                       # derivative of softplus
-        return -(ll + lp), -(g_th * dth_dx)
+        return -(ll + lp + lj), -(g_th * dth_dx)
 
 
 def map_estimate(obj, max_iters=200):

@@ -7,7 +7,8 @@ domains:
     candidates (random design, n_starting) -> batch acquisition scores -> n_anchor best -> L-BFGS-B from every anchor
     -> best optimized point.
 
-Two things differ from the reference, neither changes a number:
+Two things differ from the reference, neither changes a number (the final re-evaluation of the rounded optima, which ranks them, is
+done one point per call exactly as `apply_optimizer` does — uEI's single-point and batch branches use different incumbents when H > 1):
   * scoring + anchor selection is one fused GPU call when `f` is a bopl_b200 acquisition (anchor_points.py);
   * the per-anchor L-BFGS-B runs (the reference does them one after the other, each calling `f_df` with ONE point,
     acquisition_optimizer.py:112) run in LOCK-STEP: every anchor keeps its own, unmodified `scipy.optimize.fmin_l_bfgs_b`
@@ -291,9 +292,11 @@ class AcquisitionOptimizer(object):
             results, batches = lockstep_lbfgs(list(anchor_points), f_df, optimizer.bounds, optimizer.maxiter)
             self.last_stats = {"anchors": len(anchor_points), "f_df_batches": batches}
             if final_f:
+                # one point per call, as apply_optimizer does (optimizer.py:295-300): with H > 1 hyper-samples uEI's single-point
+                # branch (uEI.py:49-50: ONE incumbent under the model's current hyper-sample) and its batch branch (per-hyper-sample
+                # incumbents) give different values, and these values rank the optima
                 X = np.vstack([_round_optimum(self.space, r[0]) for r in results])
-                fX = np.asarray(f(X), dtype=np.float64).reshape(len(X))
-                return [(X[i:i + 1], np.atleast_2d(fX[i])) for i in range(len(X))]
+                return [(X[i:i + 1], np.atleast_2d(np.asarray(f(X[i:i + 1]), dtype=np.float64).reshape(1))) for i in range(len(X))]
             return [(r[0], r[1] if r[1] is not None else np.atleast_2d(f(r[0]))) for r in results]
         self.last_stats = {"anchors": len(anchor_points), "f_df_batches": None}
         if final_f:

@@ -6,7 +6,13 @@ block offset + local index); every rank scores its block and keeps its local top
 deterministic merge (best value first, ties -> lowest global index), so all ranks agree on the anchors without a
 second collective.  There is no data-path collective: the MC / theta reductions are per candidate.
 The reference has no counterpart (its only parallelism is a 4-process pool, uEI.py:91).
+
+On GPUs the exchange is `bopl_topk_allgather` of the C-ABI (`TopkGatherer` below): pack kernel -> one `ncclAllGather` on the compute
+stream -> merge kernel, no host synchronisation.  `allgather_topk` / `merge_topk` are the same logic over `torch.distributed` (gloo) in
+NumPy — the form the CPU tests (world_size 2) exercise, and the statement of what the device merge must return.
 """
+import ctypes
+
 import numpy as np
 
 
@@ -59,16 +65,72 @@ def allgather_topk(val, idx, x, k, group=None, device=None):
     return v[keep], i[keep], xs[keep]
 
 
+class TopkGatherer(object):
+    """The library's own NCCL communicator over the ranks of `group` + the fused pack / all-gather / merge call.
+
+    Rank 0 draws the NCCL unique id (`bopl_nccl_unique_id`), the 128 bytes travel through `torch.distributed` (whatever backend the
+    group has), every rank joins with `bopl_nccl_comm_init`.  One per engine; `close()` destroys the communicator."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        from . import _lib
+        self.engine, self.lib = engine, engine.lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _lib.check(self.lib.bopl_nccl_unique_id(ctypes.c_void_p(ident.ctypes.data)))
+        box = [ident.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+        comm = ctypes.c_void_p()
+        _lib.check(self.lib.bopl_nccl_comm_init(engine.h, self.world, self.rank, ctypes.c_void_p(ident.ctypes.data), ctypes.byref(comm)),
+                   engine.h)
+        self.comm = comm
+
+    def close(self):
+        if getattr(self, "comm", None):
+            self.lib.bopl_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+    def allgather_dev(self, val, idx, Xc, index_offset, k):
+        """Device tensors in (this rank's `Engine.topk_dev` output and its candidate block), device tensors out: the global
+        (val (k,), idx (k,), x (k,d)), identical on every rank.  Stream-ordered, no host synchronisation."""
+        import torch
+        eng = self.engine
+        k_local = int(val.shape[0])
+        val_all = eng.empty(k)
+        idx_all = torch.empty(k, dtype=torch.int64, device=eng.device)
+        x_all = eng.empty(k, eng.d)
+        eng._check(self.lib.bopl_topk_allgather(eng.h, self.comm, val.data_ptr(), idx.data_ptr(), k_local, Xc.data_ptr(),
+                                                int(index_offset), int(k), val_all.data_ptr(), idx_all.data_ptr(), x_all.data_ptr(),
+                                                eng._stream()))
+        return val_all, idx_all, x_all
+
+    def allgather_host(self, val, idx, x, k):
+        """NumPy records in (`uEI.top_candidates` output + the matching candidate rows), NumPy out; NaN-valued fillers (ranks with
+        fewer than k candidates) are dropped."""
+        eng = self.engine
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(len(val), eng.d)
+        v, i, xs = np.empty(k), np.empty(k, dtype=np.int64), np.empty((k, eng.d))
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        eng._check(self.lib.bopl_topk_allgather_host(eng.h, self.comm, p(val), p(idx), len(val), p(x), int(k), p(v), p(i), p(xs)))
+        keep = ~np.isnan(v)
+        return v[keep], i[keep], xs[keep]
+
+
 class ShardedAnchorSelector(object):
     """Scores this rank's block with `local_top(X_block, k, index_offset) -> (val, global idx)` and merges.
 
     `local_top` is `uEI.top_candidates` on a GPU box; the gloo tests inject a CPU scorer to exercise the
     partitioning + collective + merge logic without a device."""
 
-    def __init__(self, local_top, group=None, device=None):
+    def __init__(self, local_top, group=None, device=None, gatherer=None):
         self.local_top = local_top
         self.group = group
         self.device = device
+        self.gatherer = gatherer          # TopkGatherer: the exchange runs through the library's NCCL call instead of torch.distributed
 
     def select_from_full(self, X, k):
         """Every rank holds (or can generate) the full candidate matrix; it only scores its own block."""
@@ -84,4 +146,6 @@ class ShardedAnchorSelector(object):
             x = X_block[np.asarray(idx) - index_offset]
         else:
             val, idx, x = np.empty(0), np.empty(0, dtype=np.int64), np.empty((0, X_block.shape[1]))
+        if self.gatherer is not None:
+            return self.gatherer.allgather_host(val, idx, x, k)
         return allgather_topk(val, idx, x, k, self.group, self.device)

@@ -14,7 +14,9 @@
  *  - all arrays are fp64, row-major (C order).  Pointers are DEVICE pointers unless the parameter name ends
  *    in `_h` (host).  The caller owns every input/output buffer; the handle owns its copy of the model and
  *    its scratch.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
- *  - calls on one handle are stream-ordered and not thread-safe; different handles are independent.
+ *  - calls on one handle are not thread-safe; different handles are independent.  Calls on one stream are ordered by the stream;
+ *    consecutive calls on DIFFERENT streams (the host-buffer entry points run on the library's own stream) are ordered by the
+ *    library: the later stream waits for an event recorded behind the earlier call, because all calls share the handle's scratch.
  *  - there is no CPU fallback: without a CUDA device bopl_create fails.
  */
 #ifndef BOPL_B200_H
@@ -115,6 +117,11 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
                    const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
                    const double* jitter_h, int want_winv, int want_linv, double* logdet_h);
 
+/* Per-instance outcome of the last bopl_fit_model on this handle: info_h[j*H + h] = 0, or 1 + the index of the pivot that failed
+ * (that matrix is not positive definite).  Lets the caller add jitter to the FAILING matrices only, as the reference's jitchol does
+ * per matrix (GPy/util/linalg.py:53-78).  count = m*H.  HOST pointer. */
+int bopl_fit_info(const bopl_handle* h, int count, int* info_h);
+
 /* Log marginal likelihood of G independent exact GPs on the same inputs and its gradient with respect to the kernel
  * hyper-parameters — one likelihood evaluation of MAP / HMC hyper-parameter inference (GPyOpt/models/gpmodel.py:109-149 ->
  * GPy/core/gp.py:247-266: exact_gaussian_inference.py:44-65 for log p(y) and dL/dK = 0.5 (alpha alpha^T - K^-1);
@@ -214,6 +221,33 @@ int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* 
 int bopl_topk(bopl_handle* h, const double* acq, int N, int k, long long index_offset, double* val,
               long long* idx, void* stream);
 
+/* ---- multi-GPU: all-gather of the best candidates only -------------------------------------------
+ * Candidates shard row-wise over the GPUs of one box (one process and one handle per GPU); every rank scores its block and keeps its
+ * local top-k (bopl_topk).  bopl_topk_allgather then makes every rank hold the GLOBAL top-k — what the reference's single
+ * `np.argsort(scores)[:k]` over the whole batch returns (GPyOpt/optimization/anchor_points_generator.py:58-62): it packs k records
+ * (value, global index, x[d]), runs ONE ncclAllGather of k (2 + d) 8-byte words per rank on `stream`, and merges with the same
+ * deterministic kernel on every rank (value descending, ties -> lowest global index, NaN last).  Device pointers, no host
+ * synchronisation.  k_local <= k: how many of this rank's records are real (a rank with fewer than k candidates sends fillers).
+ *   val, idx [k_local]   this rank's bopl_topk output;   Xc: this rank's candidate block [N_local*d], index_offset its first global row
+ *   val_all [k], idx_all [k], x_all [k*d] (x_all may be NULL)
+ * `comm` is an ncclComm_t (as void*) spanning the ranks: the caller's own, or one made with the helpers below — rank 0 calls
+ * bopl_nccl_unique_id, ships the 128 bytes to the other ranks by any means (torch.distributed broadcast in sharding.py), every rank
+ * calls bopl_nccl_comm_init.  NCCL is bound at run time (libnccl.so.2; in a PyTorch process the copy torch loaded).
+ * bopl_topk_allgather_host is the same with HOST records in and out (x_h [k_local*d]: the rows already gathered by the caller), for
+ * callers of bopl_uei_host; it synchronises once.  bopl_topk_pack / bopl_topk_merge are the two device stages on their own (records
+ * [R*(2+d)] as bopl_topk_pack lays them out), for callers that bring their own transport. */
+int bopl_nccl_unique_id(void* id128_h);
+int bopl_nccl_comm_init(bopl_handle* h, int nranks, int rank, const void* id128_h, void** comm_out);
+int bopl_nccl_comm_destroy(void* comm);
+int bopl_topk_allgather(bopl_handle* h, void* comm, const double* val, const long long* idx, int k_local, const double* Xc,
+                        long long index_offset, int k, double* val_all, long long* idx_all, double* x_all, void* stream);
+int bopl_topk_allgather_host(bopl_handle* h, void* comm, const double* val_h, const long long* idx_h, int k_local, const double* x_h,
+                             int k, double* val_all_h, long long* idx_all_h, double* x_all_h);
+int bopl_topk_pack(bopl_handle* h, const double* val, const long long* idx, int k_local, const double* Xc, long long index_offset,
+                   int k, double* records, void* stream);
+int bopl_topk_merge(bopl_handle* h, const double* records, int R, int k, double* val_all, long long* idx_all, double* x_all,
+                    void* stream);
+
 /* ---- host-buffer convenience (the reference-facing call: NumPy arrays in, NumPy arrays out) ------------------
  * Same as bopl_uei (+ bopl_topk when k > 0) with HOST buffers; host<->device copies happen inside, chunked and
  * overlapped with compute on the handle's own streams; returns after the results are on the host.
@@ -250,6 +284,11 @@ int bopl_path_begin(bopl_handle* h, int hsel, int capacity, const double* Y_h);
 int bopl_path_eval_host(bopl_handle* h, const double* x_h, const double* z_h, double* y_h, double* mean_h, double* var_h);
 int bopl_path_length(const bopl_handle* h);
 int bopl_path_end(bopl_handle* h);
+
+/* Roofline denominator of the int8-tensor-pipe posterior kernel, measured on this handle's device: every SM issues back-to-back
+ * tcgen05.mma kind::i8 M=128 N=256 K=32 on shared-memory-resident operands for about target_ms milliseconds (<= 0: 200 ms).
+ * *tops_out = int8 tera-ops per second (2 per multiply-add), *ms_out (may be NULL) = the timed launch.  Synchronises. */
+int bopl_probe_int8_peak(bopl_handle* h, double target_ms, double* tops_out, double* ms_out);
 
 /* Number of kernel launches issued through this handle since creation (bench.py reports the delta). */
 long long bopl_launch_count(const bopl_handle* h);

@@ -142,6 +142,31 @@ def test_not_positive_definite_is_reported_and_jitter_retry_works():
     assert np.all(np.isfinite(L)) and np.all(np.isfinite(alpha))
 
 
+def test_jitter_retry_touches_only_the_failing_instance():
+    """jitchol jitters the matrix that failed, not its neighbours (GPy/util/linalg.py:53-78 is called per GP): with one singular and
+    one healthy attribute the healthy attribute's factor is bit-identical to a fit without any retry; a fit that fails for good leaves
+    the engine without a state."""
+    from bopl_b200._lib import BoplError
+    from bopl_b200.models import MultiOutputGP
+    p = make_problem("dtlz2a_quad", n=60, N=4)
+    m = p["m"]
+    X = p["X"].copy()
+    X[7:20] = X[3]
+    kinds = ["rbf"] * m
+    var, ell, noise = p["variance"].copy(), p["lengthscale"].copy(), np.full((m, 1), 1e-3)
+    good = MultiOutputGP(m, kernel=kinds, n_samples=1)
+    good.engine.fit_model(X, list(p["Y"]), kinds, var, ell, noise)
+    L_good = good.engine.get_factor(0, 0)[0]
+    var[1], ell[1], noise[1] = 1e10, 50.0, 0.0           # attribute 1: rank-deficient to working precision
+    gm = MultiOutputGP(m, kernel=kinds, n_samples=1)
+    st = gm.engine.fit_model(X, list(p["Y"]), kinds, var, ell, noise)
+    assert st.jitter[1, 0] > 0.0 and np.all(st.jitter[[0, 2, 3], 0] == 0.0)
+    assert np.array_equal(gm.engine.get_factor(0, 0)[0], L_good)
+    with pytest.raises(BoplError):
+        gm.engine.fit_model(X, list(p["Y"]), kinds, var, ell, noise, max_tries=0)
+    assert gm.engine.state is None
+
+
 @pytest.mark.parametrize("kind,ard_shared", [("Mat52", False), ("rbf", False), ("Mat32", True), ("ExpQuad", False)])
 def test_log_marginal_and_gradient_match_host_objective(kind, ard_shared):
     """`bopl_log_marginal` against the host NumPy/LAPACK likelihood of bopl_b200/fit.py (itself FD-checked in the CPU suite)

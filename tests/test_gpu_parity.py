@@ -445,6 +445,28 @@ def test_acquisition_optimizer_batched_equals_serial_on_gpu():
     assert out[0][2]["f_df_batches"] is not None
 
 
+def test_acquisition_optimizer_batched_equals_serial_with_hyper_samples():
+    """H = 3 hyper-samples: uEI's single-point branch (one stale incumbent, uEI.py:49-50) and its batch branch (per-hyper-sample
+    incumbents) differ, so the final values that rank the optima must be single-point evaluations in the lock-step driver too
+    (optimizer.py:295-300)."""
+    from bopl_b200.optimization import AcquisitionOptimizer
+    p = make_problem("dtlz1a_linear", H=3, N=300)
+    gm = gpu_model(p)
+    acq = gpu_acquisition(p, gm)
+    Xq = p["Xc"][:4]
+    one = np.vstack([acq._compute_acq(Xq[i:i + 1]) for i in range(4)])
+    assert not np.array_equal(one, acq._compute_acq(Xq))           # the two branches really differ at H > 1
+    out = []
+    for batched in (True, False):
+        np.random.seed(11)
+        gm.set_hyperparameters(0)
+        opt = AcquisitionOptimizer(acq.space, model=gm, utility=acq.utility, n_starting=300, n_anchor=5, batched=batched)
+        acq.optimizer = opt
+        x, fx = acq.optimize()
+        out.append((x, float(fx)))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
 @pytest.mark.parametrize("fname", _golden("uEIc_"))
 def test_uei_constrained_against_reference_generated_golden(fname):
     """uEI_constrained (closed-form EI x feasibility probabilities): CUDA path vs the reference's own code and vs the oracle."""

@@ -21,7 +21,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     _lib.build()
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "bopl_b200.h")).read()
-    declared = set(re.findall(r"\b(bopl_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(bopl_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -256,6 +256,34 @@ def test_hyperparameter_objective_gradient_and_map_fit():
     v, l, s = fit_hyperparameter_samples(X, Y, n_samples=4, n_burnin=10, subsample_interval=2, leapfrog_steps=5, rng=rs)
     assert v.shape == (4,) and l.shape == (4, 3) and s.shape == (4,)
     assert np.all(np.isfinite(l)) and np.all(l > 0) and np.all(v > 0) and len(np.unique(np.round(v, 12))) > 1
+
+
+def test_hyperparameter_objective_includes_the_logexp_jacobian_of_the_reference():
+    """GPy adds, for every priored parameter behind a transformation, the transform's log-Jacobian to the log prior and its gradient
+    (core/parameterization/priorizable.py:57-65,76-81; paramz 0.9.5 Logexp: log_jacobian = log(exp(theta) - 1) - theta, gradient
+    1 / (exp(theta) - 1)).  The objective is -(log p(y) + sum log Gamma(theta) + sum log_jacobian(theta)), written out here
+    independently; its gradient is checked by central differences at small theta (where the Jacobian term dominates)."""
+    from scipy.stats import gamma
+    from bopl_b200.fit import GPObjective, _softplus
+    rs = np.random.RandomState(3)
+    X = rs.uniform(size=(25, 2))
+    Y = np.cos(4 * X[:, 0]) + 0.02 * rs.normal(size=25)
+    obj = GPObjective(X, Y, "Mat52", True, None)                  # variance, 2 lengthscales, free noise
+    for x in (obj.initial(), np.array([0.3, -1.0, 0.5, -4.0]), np.array([-2.0, 1.5, -0.5, -6.0])):
+        th = _softplus(x)
+        ll, _ = obj.host_likelihood(th[0], th[1:3], th[3])
+        want = -(ll + gamma.logpdf(th, a=1.0, scale=2.0).sum() + (np.log(np.exp(th) - 1.0) - th).sum())     # Gamma.from_EV(2, 4): a = 1, b = 0.5
+        f, g = obj.value_and_grad(x)
+        assert abs(f - want) <= 1e-9 * max(1.0, abs(want)), (f, want)
+        for i in range(obj.size):
+            e = np.zeros(obj.size)
+            e[i] = 1e-6
+            fd = (obj.value_and_grad(x + e)[0] - obj.value_and_grad(x - e)[0]) / 2e-6
+            assert abs(fd - g[i]) <= 1e-5 * max(1.0, abs(fd)), (i, fd, g[i])
+    # the Jacobian term is what keeps a free noise from drifting to zero: d/dx of -(lp + lj) is negative as theta -> 0+
+    x = np.array([0.5, 0.5, 0.5, -12.0])
+    th = _softplus(x)
+    assert 1.0 / np.expm1(th[3]) > 1e4
 
 
 def test_lockstep_hyperparameter_inference_equals_per_attribute_runs():
