@@ -35,7 +35,7 @@ __device__ __forceinline__ double utility_value(const double* a, const double* t
       const double t0 = th[0];
 #pragma unroll
       for (int j = 0; j < M; ++j) u += 1.0 - exp_any(-t0 * a[j]);
-      u = u / t0 / (double)M;
+      u = u * (1.0 / (t0 * (double)M));
     }
     return u;
   }
@@ -62,7 +62,7 @@ __device__ __forceinline__ double utility_value(const double* a, const double* t
 #pragma unroll
     for (int j = 0; j < MAX_M; ++j)
       if (j < m) u += 1.0 - exp_any(-t0 * a[j]);
-    u = u / t0 / (double)m;
+    u = u * (1.0 / (t0 * (double)m));
   }
   return u;
 }
@@ -102,20 +102,25 @@ __device__ __forceinline__ void stage_small(const McParams& p, double* zs, doubl
   __syncthreads();
 }
 
-// One warp per candidate; the lanes own the MC samples (k = lane, lane+32, ...): a lane forms its posterior sample
-// a = mu + sigma * Z_k once and then sweeps the utility parameters theta_l (broadcast reads from shared memory),
-// accumulating w_l * max(U(a, theta_l) - best_l, 0).  A butterfly shuffle sums the lanes (xor pattern => every lane ends
-// with the same, order-fixed, total).
+// One warp per candidate.  The 32 lanes form a 4 x 8 grid over (sample group, theta group): a lane keeps TL utility parameters
+// (with their weights and incumbents) in REGISTERS and walks the samples k = kq, kq + 4, ...; per sample it forms the posterior
+// draw a = mu + sigma * Z_k once and evaluates its TL utilities.  The first version read theta / weight / incumbent from shared
+// memory for every (sample, theta) pair — five 8-byte shared loads per six fp64 operations, i.e. bound by the shared-memory
+// crossbar at a third of the FP64 pipe (2.4 ms per launch at the benchmark shape); now it is three broadcast loads per TL pairs.
+// Lanes then sum in a fixed order (per-lane partial sums, butterfly shuffle): bit-stable run to run.
 template <int KIND, int M>
 __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
   constexpr int MM = (M > 0) ? M : MAX_M;
+  constexpr int TL = (M > 0 && M <= 4) ? 4 : 2;                       // utility parameters per lane and pass
+  constexpr int LQ = 8, KQ = 4;                                        // lane = kq * 8 + lq
+  constexpr int PT = (KIND == BOPL_UTIL_EXPONENTIAL) ? 2 : MM;         // registers per parameter: (-theta, 1 / (theta m)) or theta[m]
   extern __shared__ double sm[];
   double* zs = sm;
   double* ths = zs + p.nw * p.m;
   double* ws = ths + p.Lt * p.p;
   double* bs = ws + p.Lt;
   stage_small(p, zs, ths, ws, bs);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, lq = lane & (LQ - 1), kq = lane / LQ;
   const int warp_global = blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * MC_WARPS;
   const int m = (M > 0) ? M : p.m;
@@ -128,25 +133,56 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
         sg[j] = sqrt(p.var[(size_t)j * p.N + c]);
       }
     double acc = 0.0;
-    for (int k = lane; k < p.nw; k += 32) {
-      double a[MM];
+    for (int l0 = 0; l0 < p.Lt; l0 += LQ * TL) {
+      double th[TL][PT], wl[TL], bl[TL], part[TL];
 #pragma unroll
-      for (int j = 0; j < MM; ++j)
-        if (j < m) a[j] = fma(sg[j], zs[k * m + j], mu[j]);
-      // two independent accumulation chains over theta (even / odd l), combined in a fixed order
-      double acc0 = 0.0, acc1 = 0.0;
-      int l = 0;
-      for (; l + 1 < p.Lt; l += 2) {
-        double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
-        double u1 = utility_value<KIND, M>(a, ths + (l + 1) * p.p, m);
-        acc0 = fma(ws[l], p.plain ? u0 : fmax(u0 - bs[l], 0.0), acc0);
-        acc1 = fma(ws[l + 1], p.plain ? u1 : fmax(u1 - bs[l + 1], 0.0), acc1);
+      for (int t = 0; t < TL; ++t) {
+        const int l = l0 + lq * TL + t;
+        const bool valid = l < p.Lt;                    // a parameter past the end: weight 0 on a harmless theta
+        if (KIND == BOPL_UTIL_EXPONENTIAL) {
+          const double t0 = valid ? ths[l] : 1.0;
+          th[t][0] = -t0;
+          th[t][1] = 1.0 / (t0 * (double)m);
+        } else {
+#pragma unroll
+          for (int j = 0; j < MM; ++j)
+            if (j < PT && j < m) th[t][j] = valid ? ths[l * p.p + j] : 0.0;
+        }
+        wl[t] = valid ? ws[l] : 0.0;
+        bl[t] = valid ? bs[l] : 0.0;
+        part[t] = 0.0;
       }
-      if (l < p.Lt) {
-        double u0 = utility_value<KIND, M>(a, ths + l * p.p, m);
-        acc0 = fma(ws[l], p.plain ? u0 : fmax(u0 - bs[l], 0.0), acc0);
+      for (int k = kq; k < p.nw; k += KQ) {
+        double a[MM];
+#pragma unroll
+        for (int j = 0; j < MM; ++j)
+          if (j < m) a[j] = fma(sg[j], zs[k * m + j], mu[j]);
+#pragma unroll
+        for (int t = 0; t < TL; ++t) {
+          double u = 0.0;
+          if (KIND == BOPL_UTIL_LINEAR) {
+#pragma unroll
+            for (int j = 0; j < MM; ++j)
+              if (j < m) u = fma(th[t][j < PT ? j : 0], a[j], u);
+          } else if (KIND == BOPL_UTIL_QUADRATIC) {
+#pragma unroll
+            for (int j = 0; j < MM; ++j)
+              if (j < m) {
+                const double df = a[j] - th[t][j < PT ? j : 0];
+                u = fma(df, df, u);
+              }
+            u = -u;
+          } else {
+#pragma unroll
+            for (int j = 0; j < MM; ++j)
+              if (j < m) u += 1.0 - exp_any(th[t][0] * a[j]);
+            u = u * th[t][1];
+          }
+          part[t] = fma(wl[t], p.plain ? u : fmax(u - bl[t], 0.0), part[t]);
+        }
       }
-      acc += acc0 + acc1;
+#pragma unroll
+      for (int t = 0; t < TL; ++t) acc += part[t];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
