@@ -20,8 +20,9 @@
 // V digit a against L digits 0..S-1-a is a single N = 64 (S - a) MMA (split at N = 256) whose output columns are exactly the
 // accumulators g = a..S-1 — 8 (10) instructions per 32-deep k-step instead of 21 (28).
 //
-// Roles (320 threads, one persistent CTA per SM): warp 0 lane 0 streams operand k-steps with cp.async.bulk (L digit images from
-// the model, V digit images from this CTA's scratch panel) through a 4-stage (3 for S = 7) ring plus one staging block per block row;
+// Roles (320 threads, one persistent CTA per SM; by default launched as clusters of two CTAs that share one candidate tile and its solved
+// panel — see the kernel's header comment): warp 0 lane 0 streams operand k-steps with cp.async.bulk (L digit images from
+// the model, V digit images from the scratch panel) through a 3- or 4-stage ring plus one staging block per block row;
 // warp 1 lane 0 issues the MMAs; warps 2-9 each own 16 candidates x the 64 rows of the block row in the DMMA C-fragment layout
 // (tcgen05.ld.16x256b delivers the accumulators in exactly that layout): K* into the fragments, accumulators recombined and
 // subtracted, inverted diagonal block applied in place on DMMA, mean and sum V^2, digits of the solved block published.
@@ -37,7 +38,7 @@ namespace bopl {
 namespace {
 
 constexpr int OB = 64;                       // rows per block row
-constexpr int OZ_MAXD = 12;                  // input dimensions the shared-memory plan is sized for
+constexpr int OZ_MAXD = MAX_D;               // input dimensions the shared-memory plan is sized for (3 ring stages; 4 fit for 6 digits and d <= 12)
 // S balanced base-256 digits hold |t| <= 127 (256^S - 1) / 255 = 0.498 * 2^(8S): a value may use up to OZ_FILL of its power-of-two scale
 constexpr double OZ_FILL = 0.995;
 constexpr int VPL = 128 * 32;                // 4096 B: one digit plane of V, 128 candidates x 32 k
@@ -49,7 +50,6 @@ struct Oz {
   static constexpr int VHALF = S * VPL;             // the S planes of one k-step
   static constexpr int VIMG = 2 * VHALF;            // per solved block
   static constexpr int OSTAGE = LHALF + VHALF;      // per pipeline stage = one k-step of one (block row, block) pair (36864 / 43008 B)
-  static constexpr int ONSTAGE = S == 6 ? 4 : 3;
 };
 constexpr int NFRAG = 36;                    // lower-triangular 8x8 blocks of a 64x64 diagonal block
 constexpr int ONT = 320;                     // producer warp, MMA warp, eight compute warps
@@ -69,9 +69,10 @@ struct OzParams {
 
 // staged per block row: Dinv B fragments, scaled training rows transposed [q][64], alpha[64], row scales[64]
 __host__ __device__ inline int oz_sb_doubles(int d) { return NFRAG * 64 + (d + 2) * OB; }
+constexpr int OZ_XBUF = 2 * 8 * 32 * 8;      // partial sums handed over inside a CTA pair: [2][compute warps][32] doubles
 template <int S>
-__host__ __device__ inline size_t oz_smem_bytes(int d) {
-  return (size_t)Oz<S>::ONSTAGE * Oz<S>::OSTAGE + (size_t)2 * oz_sb_doubles(d) * 8 + (size_t)d * 128 * 8;
+__host__ __device__ inline size_t oz_smem_bytes(int d, int nst) {
+  return (size_t)nst * Oz<S>::OSTAGE + (size_t)2 * oz_sb_doubles(d) * 8 + (size_t)d * 128 * 8 + OZ_XBUF;
 }
 
 __device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo, unsigned sbo) {
@@ -123,31 +124,91 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, int* v) {
                : "r"(taddr));
 }
 
-// TRACE: CTA 0 records clock64 at its phase boundaries into p.trace (tools/ozaki_trace.py; BOPL_OZ_TRACE=1), slot layout
+// ---- cluster-scope helpers of the row-paired launch
+__device__ __forceinline__ unsigned cluster_peer_addr(const void* p, unsigned rank) {        // same offset in the peer CTA's shared memory
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(unsigned long long* bar) {       // local barrier, visible to waiters in the peer
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.release.cluster.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void st_remote_f64(unsigned cluster_addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+// waits whose arrivals may come from the peer CTA: acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_backoff(unsigned long long* bar, unsigned parity, unsigned ns) {
+  unsigned done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
+__device__ __forceinline__ void mbar_arrive_plain(unsigned long long* bar) { mbar_arrive(bar); }
+
+// posterior_ozaki_kernel<OS digits, NST ring stages, TRACE, RP>
+//
+// RP (row-paired, the default launch): clusters of TWO CTAs work on the SAME 128-candidate tile; CTA r of the pair owns the block rows
+// i = 2 I + r of every "super-row" I.  What the pair shares is the solved panel V: for the blocks kb < 2 I both CTAs need the same V
+// k-steps, so each fetches HALF of every V k-step and multicasts it into both shared memories, while the L k-steps (its own rows) are
+// private.  The launch is bound by L2 bandwidth (profiles/r02_summary.md): per 32-deep k-step an SM pulls 14.3 (L) + 14.3 (half V) KB
+// instead of 7.2 (half L, the candidate-paired form of round 1) + 28.7 (V), and the pair keeps ONE panel (74 instead of 148 in
+// flight: they now fit the L2, so the DRAM re-reads of round 1 go away).  Block 2 I is produced by CTA 0 while the pair is in super-row
+// I and is the last block CTA 1 needs for row 2 I + 1: CTA 1 appends two private k-steps (CTA 0 walks the same two ring slots
+// without operands so that both rings stay in step).  Hand-offs inside the pair: the "block published" mbarrier of BOTH CTAs is
+// arrived on by the publishing CTA's compute warps (local + remote release.cluster arrive); ring stages are released by both MMA
+// threads (multicast tcgen05.commit); the per-candidate partial sums (mean, sum V^2: even block rows in CTA 0, odd ones in CTA 1)
+// are combined through the peer's shared memory at the end of the tile.
+// !RP: one CTA per tile, every block row; same arithmetic in the same order (partial sums of even and odd block rows are kept apart
+// and combined as the pair does), so a candidate's numbers are bit-identical in both launches.
+// TRACE (!RP only): CTA 0 records clock64 at its phase boundaries into p.trace (tools/ozaki_trace.py; BOPL_OZ_TRACE=1), slot layout
 // [row][24]: 8.. every compute warp's TMEM release, 16.. every compute warp's K* done; 0 K* start, 1 K* done, 2 accumulators full, 3 recombined (TMEM released), 4 diagonal solve done, 5 digits published
 // (compute warp 2, lane 0); 6 first MMA of the row issued, 7 last MMA of the row committed (MMA thread).  First work item only.
-// CL: launched as clusters of two CTAs that walk the same (attribute, block row, block) sequence on neighbouring candidate tiles and share
-// the factor's digit images: each CTA fetches half of every L k-step and multicasts it into both shared memories (the MMA phase is bound
-// by the L2 -> SM bandwidth: 36.9 KB per k-step and SM; the pair needs 30.7 KB).  A ring stage is free when BOTH CTAs' MMAs have read it.
-template <int OS, bool TRACE, bool CL>
+template <int OS, int NST, bool TRACE, bool RP>
 __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
-  constexpr int LIMG = Oz<OS>::LIMG, LHALF = Oz<OS>::LHALF, VHALF = Oz<OS>::VHALF, VIMG = Oz<OS>::VIMG, OSTAGE = Oz<OS>::OSTAGE,
-                ONSTAGE = Oz<OS>::ONSTAGE;
+  constexpr int LIMG = Oz<OS>::LIMG, LHALF = Oz<OS>::LHALF, VHALF = Oz<OS>::VHALF, VIMG = Oz<OS>::VIMG, OSTAGE = Oz<OS>::OSTAGE;
+  static_assert(!(TRACE && RP), "the phase trace is recorded by the single-CTA launch");
   extern __shared__ __align__(128) unsigned char osm[];
   const int d = p.d, n_pad = p.n_pad, nb = n_pad / OB;
   const int SBD = oz_sb_doubles(d);
-  unsigned char* stage_s = osm;                                              // [4][L k-step | V k-step]
-  double* SB = (double*)(osm + (size_t)ONSTAGE * OSTAGE);                    // [2][SBD]
+  unsigned char* stage_s = osm;                                              // [NST][L k-step | V k-step]
+  double* SB = (double*)(osm + (size_t)NST * OSTAGE);                        // [2][SBD]
   double* xc_s = SB + 2 * SBD;                                               // [d][128] candidates / lengthscale
-  __shared__ unsigned long long full_bar[ONSTAGE], empty_bar[ONSTAGE], sb_full[2], sb_empty[2], acc_full, tmem_empty, v_pub;
+  double* xbuf = xc_s + (size_t)d * 128;                                     // [2][NCW][32] partial sums received from the peer (RP)
+  __shared__ unsigned long long full_bar[NST], empty_bar[NST], sb_full[2], sb_empty[2], acc_full, tmem_empty, v_pub[2], x_full;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  signed char* Vpanel = p.scratch + (size_t)blockIdx.x * nb * VIMG;
 
   if (tid == 0) {
-    for (int s = 0; s < ONSTAGE; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL ? 2 : 1);
+      mbar_init(&empty_bar[s], RP ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sb_full[s], 1);
@@ -155,7 +216,9 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     }
     mbar_init(&acc_full, 1);
     mbar_init(&tmem_empty, NCW);
-    mbar_init(&v_pub, NCW * 32);
+    mbar_init(&v_pub[0], RP ? NCW : NCW * 32);   // block i is published on v_pub[i & 1]: with ONE barrier a producer of the pair could fall two
+    mbar_init(&v_pub[1], RP ? NCW : NCW * 32);   // phases behind (blocks 2 I and 2 I + 1 are both out before it asks for 2 I) and the parity would alias
+    mbar_init(&x_full, NCW);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -166,21 +229,23 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  // work items: (attribute, candidate tile), or for a cluster (attribute, pair of tiles) with CTA rank r on tile 2 pair + r (a tile past the
-  // end, when their number is odd, is computed on clamped candidates and written nowhere)
   unsigned crank = 0;
-  if (CL) {
+  if (RP) {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");   // the peer's barriers are initialised
   }
-  const int tpi = CL ? (p.ntiles + 1) / 2 : p.ntiles;          // tiles (tile pairs) per attribute
-  const int nitems = p.m * tpi;
-  const int item0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, istep = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // work items: (attribute, candidate tile), one per CTA (or per pair)
+  const int nitems = p.m * p.ntiles;
+  const int unit = RP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, istep = RP ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int item0 = unit;
+  const int RS = RP ? 2 : 1, r0 = RP ? (int)crank : 0;          // this CTA's block rows: r0, r0 + RS, ...
+  signed char* Vpanel = p.scratch + (size_t)unit * nb * VIMG;
 
   if (warp == PROD_WARP) {
     // ================================================================ producer: operand k-steps and per-block-row staging
     if (lane == 0) {
-      unsigned gc = 0, brow = 0, sc = 0;   // k-steps issued; block rows whose digits were waited for; staging blocks issued
+      unsigned gc = 0, sc = 0;             // ring slots issued; staging blocks issued
+      unsigned pubc[2] = {0, 0};           // publications waited for on v_pub[0] (even blocks) / v_pub[1] (odd blocks)
       const unsigned sb_bytes = (unsigned)SBD * 8;
       const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
       auto stage_block = [&](const GpDev& g, int i) {
@@ -190,80 +255,165 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         bulk_g2s(SB + (size_t)buf * SBD, g.OzStage + (size_t)i * SBD, sb_bytes, &sb_full[buf]);
         ++sc;
       };
-      auto load_block = [&](const signed char* Limg, int i, int kb) {      // both k-steps of block (i, kb)
+      auto wait_published = [&](int blk) {  // block blk (asked for in block order) has its digits in the panel
+        const int e = blk & 1;
+        if (RP) mbar_wait_cluster_backoff(&v_pub[e], pubc[e] & 1, 32);
+        else mbar_wait_backoff(&v_pub[e], pubc[e] & 1, 100);
+        ++pubc[e];
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+      };
+      // both k-steps of block (i, kb): the L k-step of this CTA's row, and the V k-step — whole (private) or this CTA's half, multicast
+      auto load_block = [&](const signed char* Limg, int i, int kb, bool shared_v) {
         const unsigned long long vpol = kb < p.keep_blocks ? pol_keep : pol_stream;
 #pragma unroll 1
         for (int ks = 0; ks < 2; ++ks) {
-          const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
+          const unsigned st = gc % NST, use = gc / NST;
           mbar_wait_backoff(&empty_bar[st], (use & 1) ^ 1, 100);
           unsigned char* dst = stage_s + (size_t)st * OSTAGE;
           mbar_expect_tx(&full_bar[st], OSTAGE);
-          if (CL) {      // this CTA's half (one 16-deep k-chunk of all planes) of the L k-step, into both CTAs of the pair
-            bulk_g2s_mc(dst + (size_t)crank * (LHALF / 2), Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF + (size_t)crank * (LHALF / 2),
-                        LHALF / 2, &full_bar[st], pol_keep);
-          } else {
-            bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
-          }
-          bulk_g2s_hint(dst + LHALF, Vpanel + (size_t)kb * VIMG + (size_t)ks * VHALF, VHALF, &full_bar[st], vpol);
+          bulk_g2s_hint(dst, Limg + ((size_t)i * (i - 1) / 2 + kb) * LIMG + (size_t)ks * LHALF, LHALF, &full_bar[st], pol_keep);
+          const signed char* vsrc = Vpanel + (size_t)kb * VIMG + (size_t)ks * VHALF;
+          if (RP && shared_v) bulk_g2s_mc(dst + LHALF + (size_t)crank * (VHALF / 2), vsrc + (size_t)crank * (VHALF / 2), VHALF / 2, &full_bar[st], vpol);
+          else bulk_g2s_hint(dst + LHALF, vsrc, VHALF, &full_bar[st], vpol);
           ++gc;
         }
       };
       for (int item = item0; item < nitems; item += istep) {
-        const GpDev& gp = p.gps[(item / tpi) * p.H + p.hsel];
+        const GpDev& gp = p.gps[(item / p.ntiles) * p.H + p.hsel];
         const signed char* Limg = gp.OzL;
-        if (item == item0) stage_block(gp, 0);
-        for (int i = 0; i < nb; ++i) {
-          // The staging block of row i+1 reuses the buffer of row i-1, free once that row's diagonal solve is over — which is
-          // before its digits are published: issue it behind the wait for those digits, so that the k-steps of the blocks
-          // kb < i-1 (needing neither) are prefetched while the previous block row is still being solved.
-          for (int kb = 0; kb + 1 < i; ++kb) load_block(Limg, i, kb);
-          if (i > 0) {                        // the newest block: wait until its digits are in the scratch panel
-            mbar_wait_backoff(&v_pub, brow & 1, 100);
-            ++brow;
-            asm volatile("fence.proxy.async;\n" ::: "memory");
+        if (item == item0) stage_block(gp, r0);
+        int seen = 0;                         // blocks of this item whose publication has been waited for
+        if (RP) {
+          for (int I = 0; 2 * I < nb; ++I) {
+            const int i = 2 * I + r0;
+            for (int kb = 0; kb < 2 * I; ++kb) {            // the blocks both CTAs of the pair need
+              while (seen <= kb) {
+                wait_published(seen);
+                ++seen;
+              }
+              load_block(Limg, i, kb, true);
+            }
+            // staging block of this CTA's next row: its buffer (that of the previous row) is free by now — every block up to
+            // 2 I - 1 has been published, i.e. both CTAs are past the diagonal solves of the previous super-row
+            if (i + 2 < nb) stage_block(gp, i + 2);
+            else if (item + istep < nitems) stage_block(p.gps[((item + istep) / p.ntiles) * p.H + p.hsel], r0);
+            if (r0 == 1) {                                   // block 2 I, just solved by CTA 0: private k-steps of CTA 1
+              while (seen <= 2 * I) {
+                wait_published(seen);
+                ++seen;
+              }
+              load_block(Limg, i, 2 * I, false);
+            } else {                                         // CTA 0 walks the same two ring slots without operands
+              for (int ks = 0; ks < 2; ++ks) {
+                const unsigned st = gc % NST, use = gc / NST;
+                mbar_wait_backoff(&empty_bar[st], (use & 1) ^ 1, 100);
+                mbar_arrive(&full_bar[st]);
+                ++gc;
+              }
+            }
           }
-          if (i + 1 < nb) stage_block(gp, i + 1);
-          else if (item + istep < nitems) stage_block(p.gps[((item + istep) / tpi) * p.H + p.hsel], 0);
-          if (i > 0) load_block(Limg, i, i - 1);
+          while (seen < nb) {                                // every publication is consumed once: keeps the phases in step
+            wait_published(seen);
+            ++seen;
+          }
+        } else {
+          for (int i = 0; i < nb; ++i) {
+            // The staging block of row i+1 reuses the buffer of row i-1, free once that row's diagonal solve is over — which is
+            // before its digits are published: issue it behind the wait for those digits, so that the k-steps of the blocks
+            // kb < i-1 (needing neither) are prefetched while the previous block row is still being solved.
+            for (int kb = 0; kb + 1 < i; ++kb) load_block(Limg, i, kb, false);
+            if (i > 0) {                        // the newest block: wait until its digits are in the scratch panel
+              wait_published(seen);
+              ++seen;
+            }
+            if (i + 1 < nb) stage_block(gp, i + 1);
+            else if (item + istep < nitems) stage_block(p.gps[((item + istep) / p.ntiles) * p.H + p.hsel], 0);
+            if (i > 0) load_block(Limg, i, i - 1, false);
+          }
+          wait_published(seen);                 // the last block row arrives too: keep the phases in step
+          ++seen;
         }
-        mbar_wait_backoff(&v_pub, brow & 1, 200);       // the last block row arrives too: keep the phases in step
-        ++brow;
       }
     }
   } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      unsigned gc = 0, uu = 0;            // k-steps consumed; accumulator generations started
+      unsigned gc = 0, uu = 0;            // ring slots consumed; accumulator generations completed
       const unsigned lboA = 128 * 16, lboB = OS * OB * 16, sbo = 128;
-      for (int item = item0; item < nitems; item += istep) {
-        for (int i = 1; i < nb; ++i) {
-          if (uu > 0) mbar_wait_backoff(&tmem_empty, (uu - 1) & 1, 50);     // the previous block row's accumulators have been read
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 6] = clock64();
-          for (int ks2 = 0; ks2 < 2 * i; ++ks2) {
-            const unsigned st = gc % ONSTAGE, use = gc / ONSTAGE;
-            mbar_wait_backoff(&full_bar[st], use & 1, 20);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const unsigned lk = smem_u32(stage_s + (size_t)st * OSTAGE), vb = lk + LHALF;
-            const uint32_t first = (ks2 == 0) ? 0u : 1u;
-            // V digit a (A operand, 128 candidates) x L digits 0..S-1-a (B operand rows 64 s ..) -> accumulators a..S-1 (64 columns
-            // each); an instruction covers at most 256 columns.  The a = 0 pair touches every accumulator: it clears them on the first k-step.
-            const uint64_t bl = umma_desc(lk, lboB, sbo), bh = umma_desc(lk + 4 * 1024, lboB, sbo);
+      // V digit a (A operand, 128 candidates) x L digits 0..S-1-a (B operand rows 64 s ..) -> accumulators a..S-1 (64 columns
+      // each); an instruction covers at most 256 columns.  The a = 0 pair touches every accumulator: it clears them on the first k-step.
+      auto issue_kstep = [&](unsigned st, uint32_t first) {
+        const unsigned lk = smem_u32(stage_s + (size_t)st * OSTAGE), vb = lk + LHALF;
+        const uint64_t bl = umma_desc(lk, lboB, sbo), bh = umma_desc(lk + 4 * 1024, lboB, sbo);
 #pragma unroll
-            for (int a = 0; a < OS; ++a) {
-              const uint64_t ad = umma_desc(vb + a * VPL, lboA, sbo);
-              const int ncols = 64 * (OS - a);
-              const uint32_t acc_flag = (a == 0) ? first : 1u;
-              umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols > 256 ? 256 : ncols), acc_flag);
-              if (ncols > 256) umma_i8(tmem + 64 * a + 256, ad, bh, idesc_s8(ncols - 256), acc_flag);
+        for (int a = 0; a < OS; ++a) {
+          const uint64_t ad = umma_desc(vb + a * VPL, lboA, sbo);
+          const int ncols = 64 * (OS - a);
+          const uint32_t acc_flag = (a == 0) ? first : 1u;
+          umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols > 256 ? 256 : ncols), acc_flag);
+          if (ncols > 256) umma_i8(tmem + 64 * a + 256, ad, bh, idesc_s8(ncols - 256), acc_flag);
+        }
+      };
+      for (int item = item0; item < nitems; item += istep) {
+        if (RP) {
+          for (int I = 0; 2 * I < nb; ++I) {
+            const int i = 2 * I + r0;
+            if (i > 0) {
+              if (uu > 0) mbar_wait_backoff(&tmem_empty, (uu - 1) & 1, 50);     // the previous row's accumulators have been read
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
-            if (CL) umma_commit_pair(&empty_bar[st]);
-            else umma_commit(&empty_bar[st]);
-            ++gc;
+            uint32_t done = 0;
+            for (int ks2 = 0; ks2 < 4 * I; ++ks2) {
+              const unsigned st = gc % NST, use = gc / NST;
+              mbar_wait_backoff(&full_bar[st], use & 1, 20);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+              issue_kstep(st, done);
+              done = 1u;
+              umma_commit_pair(&empty_bar[st]);
+              ++gc;
+            }
+            if (r0 == 0) {
+              if (i > 0) {
+                umma_commit(&acc_full);
+                ++uu;
+              }
+              for (int ks = 0; ks < 2; ++ks) {             // the peer's private k-steps: release the slots, nothing to multiply
+                const unsigned st = gc % NST, use = gc / NST;
+                mbar_wait_backoff(&full_bar[st], use & 1, 20);
+                umma_commit_pair(&empty_bar[st]);
+                ++gc;
+              }
+            } else {
+              for (int ks = 0; ks < 2; ++ks) {
+                const unsigned st = gc % NST, use = gc / NST;
+                mbar_wait_backoff(&full_bar[st], use & 1, 20);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                issue_kstep(st, done);
+                done = 1u;
+                umma_commit_pair(&empty_bar[st]);
+                ++gc;
+              }
+              umma_commit(&acc_full);
+              ++uu;
+            }
           }
-          umma_commit(&acc_full);
-          if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 7] = clock64();
-          ++uu;
+        } else {
+          for (int i = 1; i < nb; ++i) {
+            if (uu > 0) mbar_wait_backoff(&tmem_empty, (uu - 1) & 1, 50);     // the previous block row's accumulators have been read
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 6] = clock64();
+            for (int ks2 = 0; ks2 < 2 * i; ++ks2) {
+              const unsigned st = gc % NST, use = gc / NST;
+              mbar_wait_backoff(&full_bar[st], use & 1, 20);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+              issue_kstep(st, (ks2 == 0) ? 0u : 1u);
+              umma_commit(&empty_bar[st]);
+              ++gc;
+            }
+            umma_commit(&acc_full);
+            if (TRACE && blockIdx.x == 0 && item == item0) p.trace[i * 24 + 7] = clock64();
+            ++uu;
+          }
         }
       }
     }
@@ -273,9 +423,10 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
     const int g = lane >> 2, t = lane & 3;
     const int cbase = 32 * (warp & 3) + 16 * ((warp - 2) >> 2);   // TMEM lanes of this warp: quadrant warp % 4, half (warp-2)/4
     const uint32_t trow = tmem + ((uint32_t)cbase << 16);
-    unsigned uu = 0, sbc = 0;
-    for (int item = item0; item < nitems; item += istep) {
-      const int j = item / tpi, tile = CL ? 2 * (item - j * tpi) + (int)crank : item - j * tpi;
+    unsigned uu = 0, sbc = 0, itc = 0;
+    const unsigned peer_vpub0 = RP ? cluster_peer_addr(&v_pub[0], crank ^ 1u) : 0u;
+    for (int item = item0; item < nitems; item += istep, ++itc) {
+      const int j = item / p.ntiles, tile = item - j * p.ntiles;
       const GpDev& gp = p.gps[j * p.H + p.hsel];
       const int kind = gp.kind;
       const double variance = gp.variance;
@@ -290,9 +441,12 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         xc_s[q * 128 + cbase + c] = p.Xc[(size_t)cc * d + q] / gp.ell[q];
       }
       __syncwarp();
-      double mu[2] = {0.0, 0.0}, ss[2] = {0.0, 0.0};
+      // partial sums of this thread's two candidates over the block rows handled so far: (mu, ss) the rows of the running parity,
+      // (mu_o, ss_o) the others.  !RP: the two sets swap after every row, so at the end (nb is even) mu = even rows, mu_o = odd rows.
+      double mu[2] = {0.0, 0.0}, ss[2] = {0.0, 0.0}, mu_o[2] = {0.0, 0.0}, ss_o[2] = {0.0, 0.0};
       double acc[2][8][2];
-      for (int i = 0; i < nb; ++i) {
+#pragma unroll 1
+      for (int i = r0; i < nb; i += RS) {
         const int R0 = i * OB;
         const unsigned buf = sbc & 1;
         mbar_wait(&sb_full[buf], (sbc >> 1) & 1);
@@ -348,7 +502,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
           }
         }
 
-        // ---- subtract sum_k L_ik V_k: six s32 accumulators per (candidate, row), Horner in 2^-8, then the two power-of-two scales
+        // ---- subtract sum_k L_ik V_k: S s32 accumulators per (candidate, row), Horner in 2^-8, then the two power-of-two scales
         if (tr) p.trace[i * 24 + 1] = clock64();
         if (TRACE && blockIdx.x == 0 && item == item0 && lane == 0) p.trace[i * 24 + 16 + (warp - 2)] = clock64();     // every warp: K* done
         if (i > 0) {
@@ -483,14 +637,32 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
 #pragma unroll
             for (int s = 0; s < OS; ++s) *reinterpret_cast<uint4*>(img + (size_t)s * VPL + (size_t)mi * 128) = make_uint4(plw[s][0], plw[s][1], plw[s][2], plw[s][3]);
           }
-          // generic-proxy stores -> the producer's bulk copies (async proxy): proxy fence, then release through the mbarrier.
+          // generic-proxy stores -> the producers' bulk copies (async proxy): proxy fence, then release through the mbarrier(s).
           // (No gpu-scope __threadfence: its CCTL.IVALL / MEMBAR were 48 % of this phase's stall samples.)
           asm volatile("fence.proxy.async;\n" ::: "memory");
         }
-        mbar_arrive(&v_pub);
+        if (RP) {             // the block is published to BOTH producers of the pair: the local barrier first, then the peer's
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_release_cluster(&v_pub[i & 1]);
+            mbar_arrive_remote(peer_vpub0 + 8u * (unsigned)(i & 1));
+          }
+        } else {
+          mbar_arrive(&v_pub[i & 1]);
+        }
         if (tr) p.trace[i * 24 + 5] = clock64();
+        if (!RP) {            // next row has the other parity
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double a = mu[mi], b = ss[mi];
+            mu[mi] = mu_o[mi];
+            ss[mi] = ss_o[mi];
+            mu_o[mi] = a;
+            ss_o[mi] = b;
+          }
+        }
       }
-      // ---- finalize the item: the four t-lanes of a candidate hold its partial sums
+      // ---- finalize the item: the four t-lanes of a candidate hold its partial sums; even block rows + odd block rows
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         double v = ss[mi], w = mu[mi];
@@ -498,15 +670,52 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
         w += __shfl_xor_sync(0xffffffffu, w, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         w += __shfl_xor_sync(0xffffffffu, w, 2);
-        const int c = tile * 128 + cbase + 8 * mi + g;
-        if (t == 0 && c < p.N) {
-          const size_t o = (size_t)j * p.N + c;
-          if (p.mean) p.mean[o] = w + gp.ymean;
-          if (p.var) {
-            double vv = variance - v;
-            if (p.flags & BOPL_VAR_INCLUDE_NOISE) vv = gp.noise + vv;
-            if (p.flags & BOPL_VAR_CLIP) vv = fmax(vv, 1e-10);
-            p.var[o] = vv;
+        ss[mi] = v;
+        mu[mi] = w;
+        if (!RP) {
+          double vo = ss_o[mi], wo = mu_o[mi];
+          vo += __shfl_xor_sync(0xffffffffu, vo, 1);
+          wo += __shfl_xor_sync(0xffffffffu, wo, 1);
+          vo += __shfl_xor_sync(0xffffffffu, vo, 2);
+          wo += __shfl_xor_sync(0xffffffffu, wo, 2);
+          ss_o[mi] = vo;
+          mu_o[mi] = wo;
+        }
+      }
+      if (RP) {
+        double* xb = xbuf + (size_t)(itc & 1) * (NCW * 32) + (size_t)(warp - 2) * 32;
+        if (crank == 1) {               // odd block rows: hand the sums to CTA 0 through its shared memory
+          if (t == 0) {
+            const unsigned ra = cluster_peer_addr(xb + 4 * g, 0);
+            st_remote_f64(ra, mu[0]);
+            st_remote_f64(ra + 8, mu[1]);
+            st_remote_f64(ra + 16, ss[0]);
+            st_remote_f64(ra + 24, ss[1]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(cluster_peer_addr(&x_full, 0));
+        } else {
+          mbar_wait_cluster(&x_full, itc & 1);
+          mu_o[0] = xb[4 * g];
+          mu_o[1] = xb[4 * g + 1];
+          ss_o[0] = xb[4 * g + 2];
+          ss_o[1] = xb[4 * g + 3];
+        }
+      }
+      if (!RP || crank == 0) {
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const double v = ss[mi] + ss_o[mi], w = mu[mi] + mu_o[mi];
+          const int c = tile * 128 + cbase + 8 * mi + g;
+          if (t == 0 && c < p.N) {
+            const size_t o = (size_t)j * p.N + c;
+            if (p.mean) p.mean[o] = w + gp.ymean;
+            if (p.var) {
+              double vv = variance - v;
+              if (p.flags & BOPL_VAR_INCLUDE_NOISE) vv = gp.noise + vv;
+              if (p.flags & BOPL_VAR_CLIP) vv = fmax(vv, 1e-10);
+              p.var[o] = vv;
+            }
           }
         }
       }
@@ -514,6 +723,7 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (RP) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");   // no CTA leaves while its peer may still write into it
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
@@ -730,45 +940,47 @@ int ozaki_prepare_device(bopl_handle* h, cudaStream_t st) {
 }
 
 namespace {
-template <int S>
-int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
-  // CTA pairs (clusters of two sharing the factor's digit images) when there is enough work to keep every pair busy
-  const int npairs = (p.ntiles + 1) / 2 * h->m;
-  bool cl = h->oz_cluster != 0 && npairs >= h->sms / 2 && h->sms >= 2;
-  const long long items = cl ? 2LL * npairs : (long long)p.ntiles * h->m;
-  int grid = (int)std::min<long long>(items, h->sms);
-  if (cl) grid &= ~1;
+// One instantiation: S digits, NST ring stages.  RP launch (clusters of two CTAs per candidate tile) unless disabled or refused.
+template <int S, int NST>
+int launch_oz_n(bopl_handle* h, OzParams& p, cudaStream_t st, size_t& attr) {
+  const long long items = (long long)p.ntiles * h->m;
+  const bool rp = h->oz_cluster != 0 && h->sms >= 2;
+  const int units = (int)std::min<long long>(items, rp ? h->sms / 2 : h->sms);      // CTA pairs or CTAs, one solved panel each
+  const int grid = rp ? 2 * units : units;
   const int nb = h->n_pad / OB;
-  int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)grid * nb * Oz<S>::VIMG);
+  int rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)units * nb * Oz<S>::VIMG);
   if (rc) return rc;
   p.scratch = (signed char*)h->oz_scratch;
   {
-    // L2 budget as in posterior_trsm_t.cu: the digit image of the running attribute's factor stays resident; of the rest every CTA
+    // L2 budget as in posterior_trsm_t.cu: the digit image of the running attribute's factor stays resident; of the rest every unit
     // keeps the first blocks of its solved panel — the ones re-read most often
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
     const double limg = (double)nb * (nb - 1) / 2 * Oz<S>::LIMG;
-    const double budget = (h->trsm_l2_keep_frac * (double)l2 - 1.5 * limg) / grid;
+    const double budget = (h->trsm_l2_keep_frac * (double)l2 - 1.5 * limg) / units;
     long long blocks = (long long)(budget / (double)Oz<S>::VIMG);
     if (h->trsm_keep_blocks >= 0) blocks = h->trsm_keep_blocks;
     p.keep_blocks = (int)std::max<long long>(0, std::min<long long>(blocks, nb));
   }
-  const size_t smem = oz_smem_bytes<S>(h->d);
-  size_t& attr = h->oz_attr_smem[S - 6];
+  const size_t smem = oz_smem_bytes<S>(h->d, NST);
   if (smem > attr) {
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, NST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BOPL_CUDA(h, cudaFuncSetAttribute(posterior_ozaki_kernel<S, NST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   p.trace = nullptr;
-  if (const char* tf = getenv("BOPL_OZ_TRACE")) {      // diagnostic: phase timestamps of CTA 0's first work item -> text file
+  if (const char* tf = getenv("BOPL_OZ_TRACE")) {      // diagnostic: phase timestamps of CTA 0's first work item -> text file (single-CTA launch)
     long long* tb = nullptr;
     const size_t tbytes = (size_t)nb * 24 * sizeof(long long);
     BOPL_CUDA(h, cudaMalloc((void**)&tb, tbytes));
     BOPL_CUDA(h, cudaMemsetAsync(tb, 0, tbytes, st));
     p.trace = tb;
-    posterior_ozaki_kernel<S, true, false><<<(int)std::min<long long>((long long)p.ntiles * h->m, h->sms), ONT, smem, st>>>(p);
+    const int tgrid = (int)std::min<long long>(items, h->sms);
+    rc = ensure_bytes(h, (void**)&h->oz_scratch, &h->oz_scratch_bytes, (size_t)tgrid * nb * Oz<S>::VIMG);
+    if (rc) return rc;
+    p.scratch = (signed char*)h->oz_scratch;
+    posterior_ozaki_kernel<S, NST, true, false><<<tgrid, ONT, smem, st>>>(p);
     BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
     std::vector<long long> host((size_t)nb * 24);
     BOPL_CUDA(h, cudaStreamSynchronize(st));
@@ -782,7 +994,7 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
     }
     return BOPL_OK;
   }
-  if (cl) {
+  if (rp) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(ONT);
@@ -795,17 +1007,26 @@ int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    const cudaError_t ce = cudaLaunchKernelEx(&cfg, posterior_ozaki_kernel<S, false, true>, p);
-    if (ce != cudaSuccess) {          // a device / driver that refuses this cluster shape: same kernel, one CTA per work item, from now on
+    const cudaError_t ce = cudaLaunchKernelEx(&cfg, posterior_ozaki_kernel<S, NST, false, true>, p);
+    if (ce != cudaSuccess) {          // a device / driver that refuses this cluster shape: same arithmetic, one CTA per tile, from now on
       (void)cudaGetLastError();
       h->oz_cluster = 0;
-      return launch_oz<S>(h, p, st);
+      return launch_oz_n<S, NST>(h, p, st, attr);
     }
   } else {
-    posterior_ozaki_kernel<S, false, false><<<grid, ONT, smem, st>>>(p);
+    posterior_ozaki_kernel<S, NST, false, false><<<grid, ONT, smem, st>>>(p);
   }
   BOPL_LAUNCH_CHECK(h, "posterior_ozaki_kernel");
   return BOPL_OK;
+}
+
+template <int S>
+int launch_oz(bopl_handle* h, OzParams& p, cudaStream_t st) {
+  // four ring stages when they fit the 227 KB of shared memory (6 digits, d <= 12), else three
+  if constexpr (S == 6) {
+    if (oz_smem_bytes<S>(h->d, 4) + 512 <= 227 * 1024) return launch_oz_n<S, 4>(h, p, st, h->oz_attr_smem[0]);
+  }
+  return launch_oz_n<S, 3>(h, p, st, h->oz_attr_smem[S == 6 ? 1 : 2]);
 }
 }  // namespace
 

@@ -170,9 +170,10 @@ def test_blocked_kernels_against_reference_generated_golden(fname, kernel):
 
 
 def test_int8_cluster_pairs_equal_single_ctas_bit_for_bit(monkeypatch):
-    """Large batches run as clusters of two CTAs sharing the factor's digit images by multicast (odd tile count: the last pair has a
-    tile past the end); the arithmetic per candidate is the same, so the results equal the single-CTA launch bit for bit."""
-    p = make_problem("S", n=300, N=149 * 128 - 37)          # 149 tiles x 3 attributes >= 74 pairs: the cluster launch
+    """The default launch runs clusters of two CTAs per candidate tile (even block rows in one, odd ones in the other, the solved panel's
+    k-steps multicast into both, partial sums combined through the peer's shared memory); the arithmetic per candidate is the same in
+    the same order, so the results equal the single-CTA launch bit for bit — several tiles per pair, ragged last tile."""
+    p = make_problem("S", n=300, N=149 * 128 - 37)          # 149 tiles x 3 attributes: six work items per pair
     monkeypatch.setenv("BOPL_OZ_CLUSTER", "1")
     g1 = gpu_model(p, gradients=False, posterior_kernel="int8")
     mu1, v1 = g1.predict(p["Xc"])
@@ -217,15 +218,22 @@ def test_int8_kernel_selection_rules():
     mu_r, v_r = gm.predict(p["Xc"])
     assert np.array_equal(mu64, mu_r) and np.array_equal(v64, v_r)
     assert scaled_err(v8, v64) < 1e-9
-    # shapes the int8 kernel does not cover (d > 12) run the fp64 kernel — same library, same device, not a CPU fallback: bit-identical
+    # wide inputs (d up to 24: three ring stages) run the int8 kernels too — against the fp64 kernel of the same library
     from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
     rs = np.random.RandomState(5)
-    d, m, n = 14, 2, 90
-    X, Xc = rs.uniform(size=(n, d)), rs.uniform(size=(70, d))
-    Y = np.stack([np.sin(X @ rs.normal(size=d)) for _ in range(m)])
-    st = state_from_hyperparameters(X, Y, ["Mat52"] * m, np.ones((m, 1)), np.full((m, 1, d), 3.0), np.full((m, 1), 1e-4))
-    a, b = MultiOutputGP.from_state(st, posterior_kernel="int8"), MultiOutputGP.from_state(st, posterior_kernel="fp64")
-    assert np.array_equal(a.predict(Xc)[1], b.predict(Xc)[1])
+    for d in (14, 24):
+        m, n = 2, 200
+        X, Xc = rs.uniform(size=(n, d)), rs.uniform(size=(300, d))
+        Y = np.stack([np.sin(X @ rs.normal(size=d)) for _ in range(m)])
+        st = state_from_hyperparameters(X, Y, ["Mat52"] * m, np.ones((m, 1)), np.full((m, 1, d), 3.0), np.full((m, 1), 1e-4))
+        b = MultiOutputGP.from_state(st, posterior_kernel="fp64")
+        mu_b, v_b = b.predict(Xc)
+        for kernel, tol in (("int8", 1e-9), ("int8x7", 1e-11)):
+            a = MultiOutputGP.from_state(st, posterior_kernel=kernel)
+            assert a.engine.posterior_kernel == kernel
+            mu_a, v_a = a.predict(Xc)
+            assert not np.array_equal(v_a, v_b)              # it is the int8 kernel that ran
+            assert scaled_err(mu_a, mu_b) < 1e-12 and rel_err(v_a, v_b) < tol, (d, kernel, rel_err(v_a, v_b))
 
 
 @pytest.mark.parametrize("kernel", ["int8"])

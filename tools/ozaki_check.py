@@ -1,10 +1,9 @@
-"""INT8-tensor-pipe posterior kernel (BOPL_TRSM_VARIANT=4, BOPL_OZAKI=1) against the fp64 DMMA kernel and the oracle.
-usage: python tools/ozaki_check.py n N [time]"""
+"""INT8-tensor-pipe posterior kernel ($OZ_KERNEL = int8x7 (default) | int8; $BOPL_OZ_CLUSTER=0: single-CTA launch) against the fp64
+DMMA kernel and the oracle.   usage: python tools/ozaki_check.py n N [time]"""
 import os
 import sys
 import time
 
-os.environ["BOPL_OZAKI"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -15,10 +14,8 @@ from tests.helpers import gpu_model, oracle_model
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 p = make_problem("S", n=n, N=N)
-os.environ["BOPL_TRSM_VARIANT"] = "4"
-goz = gpu_model(p)
-os.environ["BOPL_TRSM_VARIANT"] = "3"
-gdm = gpu_model(p)
+goz = gpu_model(p, gradients=False, posterior_kernel=os.environ.get("OZ_KERNEL", "int8x7"))
+gdm = gpu_model(p, gradients=False, posterior_kernel="fp64")
 mo, vo = goz.predict(p["Xc"])
 md, vd = gdm.predict(p["Xc"])
 print("ozaki vs dmma: mean %.3e  var rel %.3e" % (np.max(np.abs(mo - md)) / np.max(np.abs(md)), np.max(np.abs(vo - vd) / np.abs(vd))), flush=True)
