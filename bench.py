@@ -171,7 +171,7 @@ def _events(torch, n):
     return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
 
 
-def measure_peaks(torch, eng, dev):
+def measure_peaks(torch, eng, dev, index=0):
     """The two roofline denominators, measured in this run on this device (each about a second)."""
     import ctypes
     out = {}
@@ -192,10 +192,24 @@ def measure_peaks(torch, eng, dev):
     out["fp64_dgemm_how"] = "torch.matmul fp64 8192^3 (cuBLAS), best of 10, CUDA events"
     del a, b
     torch.cuda.empty_cache()
+    # int8 tensor pipe: back-to-back 150 ms launches of the issue loop for ~3 s.  "burst" = the fastest launch (a kernel timed alone, cool
+    # chip), "sustained" = the mean of the last second (a kernel inside a long step: the board sits at its 1 kW power cap and the SM
+    # clock settles well below 1965 MHz, exactly as MEASURED_PEAKS.json reports for the cuBLAS bf16 GEMM)
     tops, ms = ctypes.c_double(), ctypes.c_double()
-    eng._check(eng.lib.bopl_probe_int8_peak(eng.h, 300.0, ctypes.byref(tops), ctypes.byref(ms)))
-    out["int8_tops"] = tops.value
-    out["int8_how"] = "bopl_probe_int8_peak: back-to-back tcgen05.mma kind::i8 M=128 N=256 K=32 on resident operands, all SMs, %.0f ms" % ms.value
+    rates, t_end = [], time.perf_counter() + 3.0
+    sampler = ClockSampler(index)
+    sampler.start()
+    while time.perf_counter() < t_end:
+        eng._check(eng.lib.bopl_probe_int8_peak(eng.h, 150.0, ctypes.byref(tops), ctypes.byref(ms)))
+        rates.append((time.perf_counter(), tops.value))
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+    out["int8_probe_clocks"] = sampler.summary()
+    last = [r for t, r in rates if t >= rates[-1][0] - 1.0]
+    out["int8_tops_burst"] = max(r for _, r in rates)
+    out["int8_tops_sustained"] = float(np.mean(last))
+    out["int8_how"] = ("bopl_probe_int8_peak: back-to-back tcgen05.mma kind::i8 M=128 N=256 K=32 on resident operands, all SMs, %d launches of "
+                       "~150 ms over 3 s; burst = fastest launch, sustained = mean of the last second (power cap)" % len(rates))
     return out
 
 
@@ -344,10 +358,14 @@ def run_gpu(args):
                            "source": "profiles/r01_fp64_peaks.json, profiles/r01_int8_peaks.json (round 1, another lease)"}
         peaks_now = None
         if world == 1 and not args.no_extras:
-            peaks_now = measure_peaks(torch, eng, dev)
+            peaks_now = measure_peaks(torch, eng, dev, local_rank)
         peak_tf = peaks_now["fp64_dgemm_tflops"] if peaks_now else peaks_committed["fp64_dgemm_tflops"]
-        peak_i8 = peaks_now["int8_tops"] if peaks_now else peaks_committed["int8_tops"]
-        peak_src = "measured in this run (roofline.peak_measured_this_run)" if peaks_now else peaks_committed["source"]
+        # the posterior kernel is timed INSIDE a long step (back-to-back 180 ms launches at the power cap): the sustained figure is its
+        # denominator (B200_PROFILING.md); the burst figure is reported beside it (roofline.frac_of_burst_peak)
+        peak_i8 = peaks_now["int8_tops_sustained"] if peaks_now else peaks_committed["int8_tops"]
+        peak_i8_burst = peaks_now["int8_tops_burst"] if peaks_now else peaks_committed["int8_tops"]
+        peak_src = ("measured in this run (roofline.peak_measured_this_run): int8 SUSTAINED issue rate under the power cap; DGEMM best of 10"
+                    if peaks_now else peaks_committed["source"])
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "trsm_traffic.json")
         if os.path.exists(tpath):
@@ -369,7 +387,7 @@ def run_gpu(args):
             r = {"bound": "tensor",
                  "kernel": "posterior_ozaki_kernel<%d> (fused K*, blocked triangular solve with the n^2/2 update as %d exact int8 digit products "
                            "per fp64 multiply-add on tcgen05.mma kind::i8 / TMEM, fp64 diagonal solve on DMMA, mean, variance)" % (S, S * (S + 1) // 2),
-                 "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8,
+                 "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8, "frac_of_burst_peak": ach / peak_i8_burst,
                  "unit_note": "int8 tensor tera-ops/s (2 per multiply-add); algorithmic ops = 2 * %d * m * N * n^2/2" % (S * (S + 1) // 2),
                  "kernel_ms": kernel_ms, "int8_ops_per_launch": ops, "flops_per_launch": flops,
                  "fp64_equivalent": {"achieved": fp64_equiv, "peak": peak_tf, "unit": "TFLOP/s", "frac": fp64_equiv / peak_tf,
@@ -475,7 +493,7 @@ def run_extras(args, torch, dev, local_rank, p, state, model, Xd, flush, rooflin
         ms = time_calls(lambda: eng.posterior_dev(Xd, 0))
         _, var = eng.posterior_dev(Xd, 0)
         rec = roofline_of(kind, ms, N)
-        rec = {k: rec[k] for k in ("kernel", "kernel_ms", "achieved", "peak", "unit", "frac") + (("time_shared_bound",) if kind != "fp64" else ())}
+        rec = {k: rec[k] for k in ("kernel", "kernel_ms", "achieved", "peak", "unit", "frac") + (("frac_of_burst_peak", "time_shared_bound") if kind != "fp64" else ())}
         rec["evals_per_s_if_it_were_the_step"] = float(N) * w["n_w"] * w["L"] / (ms * 1e-3)
         if kind == "fp64":
             var64 = var
