@@ -15,7 +15,7 @@ __device__ __forceinline__ uint64_t probe_desc(unsigned saddr, unsigned lbo, uns
          ((uint64_t)1 << 46);
 }
 
-// A [128 x 128] and B [256 x 128] int8 images (K-major core-matrix layout; the values do not matter for the rate) in shared memory;
+// A [128 x 128] and B [256 x 128] int8 images (K-major core-matrix layout, pseudo-random bytes) in shared memory;
 // thread 0 issues `reps` rounds of the four 32-deep k-steps, alternating between two accumulator ranges.
 __global__ void __launch_bounds__(128, 1) int8_peak_kernel(int reps) {
   extern __shared__ __align__(1024) unsigned char psm[];
@@ -23,7 +23,20 @@ __global__ void __launch_bounds__(128, 1) int8_peak_kernel(int reps) {
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int K = 128, N = 256;
-  for (int i = tid; i < (128 + N) * K / 16; i += 128) reinterpret_cast<uint4*>(psm)[i] = make_uint4(0x01010101u * (i & 3), 0x02020202u, 0x01010101u, 0u);
+  // pseudo-random digits (full int8 range, like the kernel's balanced digits): constant operands would understate the pipe's power
+  // draw, and with it overstate the clock the board sustains under its power cap
+  for (int i = tid; i < (128 + N) * K / 16; i += 128) {
+    uint32_t x = (uint32_t)i * 2654435761u + blockIdx.x * 40503u + 12345u;
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x ^= x << 13;
+      x ^= x >> 17;
+      x ^= x << 5;
+      w[u] = x;
+    }
+    reinterpret_cast<uint4*>(psm)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
