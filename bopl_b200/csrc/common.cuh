@@ -64,7 +64,8 @@ struct bopl_handle {
   double* trsm_scratch = nullptr; size_t trsm_scratch_bytes = 0;   // per-CTA V panels
   double* mean_s = nullptr; double* var_s = nullptr; size_t mean_bytes = 0, var_bytes = 0;        // [m*N]
   double* dmean_s = nullptr; double* dvar_s = nullptr; size_t dmean_bytes = 0, dvar_bytes = 0;    // [m*N*d]
-  double* grad_scratch = nullptr; size_t grad_scratch_bytes = 0;               // K*, G, beta panels of the gradient path
+  double* grad_scratch = nullptr; size_t grad_scratch_bytes = 0;               // K*, G, beta panels + padded Winv of the gradient path
+  bool gemm_attr_set = false;
   double* acq_s = nullptr; size_t acq_cap = 0;                                 // [N] (host path / top-k only callers)
   double* F_s = nullptr; size_t F_bytes = 0; bool F_valid = false;             // [H*m*n] posterior mean at the training points
   double* topk_val_s = nullptr; long long* topk_idx_s = nullptr; size_t topk_cap = 0;

@@ -5,7 +5,7 @@
 //   grad_contract_kernel    d mu / dx and d var / dx                      (GPy/kern/src/stationary.py:312-322)
 // Reference: GPy/kern/src/stationary.py:104-171,227-254,312-342; GPy/core/gp.py:380-400,438-490;
 // inference/latent_function_inference/posterior.py:299-305.
-#include "common.cuh"
+#include "pipeline.cuh"
 
 namespace bopl {
 
@@ -18,7 +18,7 @@ constexpr int KS_NT = 256;
 
 template <bool WITH_G>
 __global__ void __launch_bounds__(KS_NT) kstar_kernel(GpDev gp, const double* __restrict__ Xc, int N, int d, int n, int pad,
-                                                       double* __restrict__ K, double* __restrict__ G) {
+                                                       double* __restrict__ K, double* __restrict__ G, int ldk) {
   __shared__ double xc_s[KS_TC * MAX_D];
   const int c0 = blockIdx.x * KS_TC;
   for (int idx = threadIdx.x; idx < KS_TC * d; idx += KS_NT) {
@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(KS_NT) kstar_kernel(GpDev gp, const double* __
       if (WITH_G) {
         double k, g;
         kern_value_grad(gp.kind, gp.variance, r2, k, g);
-        K[(size_t)(c0 + c) * n + i] = k;
+        K[(size_t)(c0 + c) * ldk + i] = k;
         G[(size_t)(c0 + c) * n + i] = g;
       } else {
-        K[(size_t)(c0 + c) * n + i] = kern_value(gp.kind, gp.variance, r2);
+        K[(size_t)(c0 + c) * ldk + i] = kern_value(gp.kind, gp.variance, r2);
       }
     }
   }
@@ -115,55 +115,90 @@ __global__ void __launch_bounds__(PM_TC* PM_RG) posterior_mean_kernel(MeanParams
 // B[Nc x n] = -2 * K[Nc x n] * Winv[n x n] on the FP64 tensor pipe (DMMA.8x8x4), for every batch size: an output
 // element's accumulation order does not depend on the other rows of the batch, so a candidate's gradient is bit-identical
 // whether it is evaluated alone (the L-BFGS call shape) or inside a batch (the lock-step multi-start driver relies on it).
-// CTA tile 64 (cands) x 64 (cols), k-step 16, 4 warps (2 x 2), warp tile 32 x 32 = 16 accumulators.
-constexpr int GM_BM = 64, GM_BN = 64, GM_BK = 16, GM_NT = 128;
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+// beta = -2 K* Winv (GPy/core/gp.py:474) as a DMMA tile product in the form of posterior_trsm_t.cu's main loop: CTA tile 128 candidates x
+// 128 columns, k-step 16, eight warps each owning 16 candidates x all 128 columns (2 x 16 DMMA.8x8x4 accumulator tiles), operands through
+// a 3-stage cp.async ring of 128 x 16 tiles in the 16-byte XOR-swizzled layout (conflict-free LDS.128 fragments; the two halves of a
+// double2 feed two DMMAs with the k-sets {0,2,..} / {1,3,..} on both operands).  Operands are PADDED copies: K* [chunk x ldk] with zero
+// columns up to a multiple of 16 (kstar_kernel writes it that way), Winv [rows up to a multiple of 128 x ldk] (winv_pad_kernel) — Winv is
+// symmetric, so its row j is column j read K-major.  Per output element the k order is fixed: a candidate's beta is bit-identical in
+// any batch above the small-batch limit.  Round 1's 64 x 64 tile kernel with synchronous loads ran at 0.33 of the DGEMM peak.
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_NT = 256, GM_STAGES = 3;
+constexpr int GM_TILE = GM_BM * GM_BK;                    // doubles per operand tile
+constexpr size_t GM_SMEM = (size_t)GM_STAGES * 2 * GM_TILE * sizeof(double);
+
+__global__ void winv_pad_kernel(const double* __restrict__ W, int n, double* __restrict__ WP, int rows, int ldk) {
+  const size_t total = (size_t)rows * ldk;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / ldk), c = (int)(e - (size_t)r * ldk);
+    WP[e] = (r < n && c < n) ? W[(size_t)r * n + c] : 0.0;
+  }
 }
-__global__ void __launch_bounds__(GM_NT) beta_gemm_kernel(const double* __restrict__ Winv, const double* __restrict__ K, int nc,
-                                                           int n, double* __restrict__ B) {
-  // As[m][k] (k contiguous, +1 pad), Bs[k][nn] from Winv[k][col] (symmetric => also Winv[col][k]); store as Bs[nn][k].
-  __shared__ double As[GM_BM][GM_BK + 1];
-  __shared__ double Bs[GM_BN][GM_BK + 1];
+
+__global__ void __launch_bounds__(GM_NT, 1) beta_gemm_kernel(const double* __restrict__ WP, const double* __restrict__ K, int nc, int n,
+                                                             int ldk, double* __restrict__ B) {
+  extern __shared__ __align__(128) double gsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;
+  const int Cw = warp * 16, swz = (g & 1) << 2;
   const int r0 = blockIdx.y * GM_BM, col0 = blockIdx.x * GM_BN;
-  double acc[4][4][2];
+  const double* Arow = K + (size_t)r0 * ldk;              // candidates r0 .. r0 + 127 (the K* buffer holds whole 128-row tiles)
+  const double* Brow = WP + (size_t)col0 * ldk;           // columns col0 .. col0 + 127 as rows of the symmetric matrix
+  const int nsteps = ldk / GM_BK;
+  double acc[2][16][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
-  for (int k0 = 0; k0 < n; k0 += GM_BK) {
-    __syncthreads();
-    for (int idx = tid; idx < GM_BM * GM_BK; idx += GM_NT) {
-      int r = idx / GM_BK, k = idx - r * GM_BK;
-      As[r][k] = (r0 + r < nc && k0 + k < n) ? K[(size_t)(r0 + r) * n + k0 + k] : 0.0;
-      // Winv symmetric: element (k0+k, col0+r) == (col0+r, k0+k): read row (col0+r) contiguously along k
-      Bs[r][k] = (col0 + r < n && k0 + k < n) ? Winv[(size_t)(col0 + r) * n + k0 + k] : 0.0;
-    }
-    __syncthreads();
+    for (int nt = 0; nt < 16; ++nt) acc[mi][nt][0] = acc[mi][nt][1] = 0.0;
+  auto issue = [&](int it) {
+    double* As = gsm + (size_t)(it % GM_STAGES) * 2 * GM_TILE;
+    load_tile<GM_BM, GM_BK, GM_NT>(As, Arow + (size_t)it * GM_BK, ldk, tid);
+    load_tile<GM_BN, GM_BK, GM_NT>(As + GM_TILE, Brow + (size_t)it * GM_BK, ldk, tid);
+  };
 #pragma unroll
-    for (int kk = 0; kk < GM_BK; kk += 4) {
-      double a[4], b[4];
+  for (int s = 0; s < GM_STAGES - 1; ++s) {
+    if (s < nsteps) issue(s);
+    cp_async_commit();
+  }
+  for (int it = 0; it < nsteps; ++it) {
+    cp_async_wait<GM_STAGES - 2>();
+    __syncthreads();                       // tile `it` has landed for every thread; every warp is past tile it - 1: its buffer may be refilled
+    if (it + GM_STAGES - 1 < nsteps) issue(it + GM_STAGES - 1);
+    cp_async_commit();
+    const double* As = gsm + (size_t)(it % GM_STAGES) * 2 * GM_TILE;
+    const double* Bs = As + GM_TILE;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + 8 * i + g][kk + t];
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ch = ((t + 4 * kk) ^ swz) << 1;
+      double2 a[2];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) b[jj] = Bs[wn * 32 + 8 * jj + g][kk + t];
+      for (int mi = 0; mi < 2; ++mi) a[mi] = *reinterpret_cast<const double2*>(As + (Cw + 8 * mi + g) * GM_BK + ch);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int hf = 0; hf < 2; ++hf) {
+        double2 b[8];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+        for (int u = 0; u < 8; ++u) b[u] = *reinterpret_cast<const double2*>(Bs + (8 * (8 * hf + u) + g) * GM_BK + ch);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) dmma(acc[mi][8 * hf + u][0], acc[mi][8 * hf + u][1], a[mi].x, b[u].x);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) dmma(acc[mi][8 * hf + u][0], acc[mi][8 * hf + u][1], a[mi].y, b[u].y);
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int mi = 0; mi < 2; ++mi) {
+    const int r = r0 + Cw + 8 * mi + g;
+    if (r >= nc) continue;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
+    for (int nt = 0; nt < 16; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        int r = r0 + wm * 32 + 8 * i + g, cidx = col0 + wn * 32 + 8 * jj + 2 * t + e;
-        if (r < nc && cidx < n) B[(size_t)r * n + cidx] = -2.0 * acc[i][jj][e];
+        const int cidx = col0 + 8 * nt + 2 * t + e;
+        if (cidx < n) B[(size_t)r * n + cidx] = -2.0 * acc[mi][nt][e];
       }
+  }
 }
 
 // --------------------------------------------------------------------------------------------- gradient contraction
@@ -449,7 +484,7 @@ int launch_cross_cov(bopl_handle* h, const double* Xc, int N, int hsel, int j, d
   if (N <= 0) return BOPL_OK;
   const GpDev& gp = h->gp_host[j * h->H + hsel];
   dim3 grid((N + KS_TC - 1) / KS_TC, std::max(1, std::min(8, (h->n + KS_NT - 1) / KS_NT)));
-  kstar_kernel<false><<<grid, KS_NT, 0, st>>>(gp, Xc, N, h->d, h->n, h->pad, K, nullptr);
+  kstar_kernel<false><<<grid, KS_NT, 0, st>>>(gp, Xc, N, h->d, h->n, h->pad, K, nullptr, h->n);
   BOPL_LAUNCH_CHECK(h, "kstar_kernel");
   return BOPL_OK;
 }
@@ -561,24 +596,36 @@ int launch_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, dou
   if (N <= 0) return BOPL_OK;
   if (use_small_path(h, N)) return launch_posterior_grad_small(h, Xc, N, hsel, dmean, dvar, st);
   const int n = h->n, d = h->d;
-  const int chunk = std::min(N, 2048);
-  size_t need = (size_t)3 * chunk * n * sizeof(double);
+  const int chunk = 2048;                                          // whole 128-row tiles of the beta GEMM
+  const int ldk = (n + GM_BK - 1) / GM_BK * GM_BK, wrows = (n + GM_BN - 1) / GM_BN * GM_BN;
+  const size_t kb_cnt = (size_t)chunk * ldk, gb_cnt = (size_t)chunk * n, wp_cnt = dvar ? (size_t)wrows * ldk : 0;
+  size_t need = (kb_cnt + 2 * gb_cnt + wp_cnt) * sizeof(double);
   int rc = ensure_bytes(h, (void**)&h->grad_scratch, &h->grad_scratch_bytes, need);
   if (rc) return rc;
-  double* Kb = h->grad_scratch;
-  double* Gb = Kb + (size_t)chunk * n;
-  double* Bb = Gb + (size_t)chunk * n;
+  double* Kb = h->grad_scratch;                                    // K* [chunk x ldk], zero beyond column n
+  double* Gb = Kb + kb_cnt;
+  double* Bb = Gb + gb_cnt;
+  double* WP = Bb + gb_cnt;                                        // zero-padded copy of the running attribute's Winv
+  BOPL_CUDA(h, cudaMemsetAsync(Kb, 0, kb_cnt * sizeof(double), st));
+  if (dvar && !h->gemm_attr_set) {
+    BOPL_CUDA(h, cudaFuncSetAttribute(beta_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
+    h->gemm_attr_set = true;
+  }
   for (int j = 0; j < h->m; ++j) {
     const GpDev& gp = h->gp_host[j * h->H + hsel];
+    if (dvar) {
+      winv_pad_kernel<<<h->sms * 4, 256, 0, st>>>(gp.Winv, n, WP, wrows, ldk);
+      BOPL_LAUNCH_CHECK(h, "winv_pad_kernel");
+    }
     for (int s = 0; s < N; s += chunk) {
       const int nc = std::min(chunk, N - s);
       const double* xc = Xc + (size_t)s * d;
       dim3 gridk((nc + KS_TC - 1) / KS_TC, std::max(1, std::min(8, (n + KS_NT - 1) / KS_NT)));
-      kstar_kernel<true><<<gridk, KS_NT, 0, st>>>(gp, xc, nc, d, n, h->pad, Kb, Gb);
+      kstar_kernel<true><<<gridk, KS_NT, 0, st>>>(gp, xc, nc, d, n, h->pad, Kb, Gb, ldk);
       BOPL_LAUNCH_CHECK(h, "kstar_kernel<G>");
       if (dvar) {
-        dim3 gg((n + GM_BN - 1) / GM_BN, (nc + GM_BM - 1) / GM_BM);
-        beta_gemm_kernel<<<gg, GM_NT, 0, st>>>(gp.Winv, Kb, nc, n, Bb);
+        dim3 gg(wrows / GM_BN, (nc + GM_BM - 1) / GM_BM);
+        beta_gemm_kernel<<<gg, GM_NT, GM_SMEM, st>>>(WP, Kb, nc, n, ldk, Bb);
         BOPL_LAUNCH_CHECK(h, "beta_gemm_kernel");
       }
       grad_contract_kernel<<<nc, GC_NT, 0, st>>>(gp, h->X_dev, xc, d, n, h->pad, Gb, dvar ? Bb : nullptr,

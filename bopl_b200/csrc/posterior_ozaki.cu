@@ -344,14 +344,19 @@ __global__ void __launch_bounds__(ONT, 1) posterior_ozaki_kernel(OzParams p) {
       // each); an instruction covers at most 256 columns.  The a = 0 pair touches every accumulator: it clears them on the first k-step.
       auto issue_kstep = [&](unsigned st, uint32_t first) {
         const unsigned lk = smem_u32(stage_s + (size_t)st * OSTAGE), vb = lk + LHALF;
-        const uint64_t bl = umma_desc(lk, lboB, sbo), bh = umma_desc(lk + 4 * 1024, lboB, sbo);
+        const uint64_t bl = umma_desc(lk, lboB, sbo);
 #pragma unroll
         for (int a = 0; a < OS; ++a) {
           const uint64_t ad = umma_desc(vb + a * VPL, lboA, sbo);
           const int ncols = 64 * (OS - a);
           const uint32_t acc_flag = (a == 0) ? first : 1u;
-          umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols > 256 ? 256 : ncols), acc_flag);
-          if (ncols > 256) umma_i8(tmem + 64 * a + 256, ad, bh, idesc_s8(ncols - 256), acc_flag);
+          if (ncols > 256) {      // two instructions of (nearly) equal width — 224 + 224, 192 + 192, 160 + 160 — rather than 256 + a narrow rest: N = 64 issues at 65 % of the N = 256 rate
+            const int n1 = ((ncols / 2 + 15) / 16) * 16;
+            umma_i8(tmem + 64 * a, ad, bl, idesc_s8(n1), acc_flag);
+            umma_i8(tmem + 64 * a + n1, ad, umma_desc(lk + 16 * n1, lboB, sbo), idesc_s8(ncols - n1), acc_flag);
+          } else {
+            umma_i8(tmem + 64 * a, ad, bl, idesc_s8(ncols), acc_flag);
+          }
         }
       };
       for (int item = item0; item < nitems; item += istep) {

@@ -81,12 +81,47 @@ def uei_df_floor(om, p, X):
     return np.abs(pert - base)
 
 
+PARITY_REPORT = {}
+
+
+def _report(what, got, want, scale):
+    """Achieved errors of every check_close call: relative to the array's scale, and ELEMENT-relative over the entries above 1e-6 of
+    the scale (entries that are exactly or nearly zero — EI far from the incumbent — have no meaningful relative error).  Written to
+    gpurun_out/parity_report.json at the end of the session (conftest-free: atexit), committed as profiles/r02_parity_report.json."""
+    import atexit
+    import json
+    import os
+    err = np.abs(got - want)
+    big = (np.abs(want) >= 1e-6 * scale) & (np.abs(want) > 0.0)
+    rec = {"scale_rel": float(err.max() / max(scale, 1e-300)) if err.size else 0.0,
+           "elem_rel_above_1e-6_of_scale": float(np.max(err[big] / np.abs(want[big]))) if np.any(big) else 0.0,
+           "entries": int(err.size), "entries_above_1e-6_of_scale": int(np.sum(big))}
+    first = not PARITY_REPORT
+    key = what
+    k = 1
+    while key in PARITY_REPORT:
+        k += 1
+        key = "%s #%d" % (what, k)
+    PARITY_REPORT[key] = rec
+    if first:
+        def dump():
+            out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+            if os.path.isdir(out_dir):
+                worst = max(PARITY_REPORT.values(), key=lambda r: r["elem_rel_above_1e-6_of_scale"])
+                with open(os.path.join(out_dir, "parity_report.json"), "w") as f:
+                    json.dump({"worst_elem_rel_above_1e-6_of_scale": worst["elem_rel_above_1e-6_of_scale"],
+                               "worst_scale_rel": max(r["scale_rel"] for r in PARITY_REPORT.values()), "checks": PARITY_REPORT}, f, indent=1)
+        atexit.register(dump)
+
+
 def check_close(got, want, what, rtol=RTOL):
     got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, (what, got.shape, want.shape)
     scale = float(np.max(np.abs(want))) if want.size else 0.0
     err = np.abs(got - want)
     tol = rtol * np.maximum(np.abs(want), scale)
+    if want.size:
+        _report(what, got, want, scale)
     assert np.all(err <= tol), "%s: max err %.3e (scale %.3e, rel-to-scale %.3e)" % (what, err.max(), scale, err.max() / max(scale, 1e-300))
 
 
