@@ -78,6 +78,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super(ClockSampler, self).__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.sm_max, self.err = index, False, [], set(), None, None
+        self.power, self.power_limit = [], None
 
     def run(self):
         try:
@@ -85,8 +86,16 @@ class ClockSampler(threading.Thread):
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:
+                self.power_limit = None
             while not self.stop_flag:
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, nm in self.REASONS.items():
@@ -98,7 +107,9 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), **({"error": self.err} if self.err else {})}
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w": float(np.median(self.power)) if self.power else None, "power_w_max": float(np.max(self.power)) if self.power else None,
+                "power_limit_w": self.power_limit, **({"error": self.err} if self.err else {})}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -482,19 +493,31 @@ def run_extras(args, torch, dev, local_rank, p, state, model, Xd, flush, rooflin
             ms.append(e[0].elapsed_time(e[1]))
         return float(np.mean(ms))
 
-    # (1) the three posterior kernels on the same inputs: launch time, roofline fraction, variance difference from the fp64 kernel
+    # (1) the three posterior kernels on the same inputs (+ the default kernel launched one CTA per tile instead of as row-paired clusters):
+    # launch time, roofline fraction, SM clock and board power while they run, variance difference from the fp64 kernel
     models = {model.engine.posterior_kernel: model}
     for kind in ("int8x7", "fp64", "int8"):
         if kind not in models:
             models[kind] = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel=kind)
+    os.environ["BOPL_OZ_CLUSTER"] = "0"
+    models["int8x7_single_cta"] = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel="int8x7")
+    del os.environ["BOPL_OZ_CLUSTER"]
     kernels, var64 = {}, None
-    for kind in ("fp64", "int8x7", "int8"):
+    for kind in ("fp64", "int8x7", "int8", "int8x7_single_cta"):
         eng = models[kind].engine
-        ms = time_calls(lambda: eng.posterior_dev(Xd, 0))
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms = time_calls(lambda: eng.posterior_dev(Xd, 0), reps=4)
+        sampler.stop_flag = True
+        sampler.join(timeout=2.0)
         _, var = eng.posterior_dev(Xd, 0)
-        rec = roofline_of(kind, ms, N)
-        rec = {k: rec[k] for k in ("kernel", "kernel_ms", "achieved", "peak", "unit", "frac") + (("frac_of_burst_peak", "time_shared_bound") if kind != "fp64" else ())}
+        base = kind.split("_")[0]
+        rec = roofline_of(base, ms, N)
+        rec = {k: rec[k] for k in ("kernel", "kernel_ms", "achieved", "peak", "unit", "frac") + (("frac_of_burst_peak", "time_shared_bound") if base != "fp64" else ())}
         rec["evals_per_s_if_it_were_the_step"] = float(N) * w["n_w"] * w["L"] / (ms * 1e-3)
+        rec["clocks"] = sampler.summary()
+        if kind == "int8x7_single_cta":
+            rec["launch"] = "BOPL_OZ_CLUSTER=0: one CTA per candidate tile, 148 solved panels (bit-identical results)"
         if kind == "fp64":
             var64 = var
         else:

@@ -109,7 +109,7 @@ __device__ __forceinline__ void stage_small(const McParams& p, double* zs, doubl
 // crossbar at a third of the FP64 pipe (2.4 ms per launch at the benchmark shape); now it is three broadcast loads per TL pairs.
 // Lanes then sum in a fixed order (per-lane partial sums, butterfly shuffle): bit-stable run to run.
 template <int KIND, int M>
-__global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
+__global__ void __launch_bounds__(MC_NT, (M > 0 && M <= 4) ? 2 : 1) uei_mc_kernel(McParams p) {
   constexpr int MM = (M > 0) ? M : MAX_M;
   constexpr int TL = (M > 0 && M <= 4) ? 4 : 2;                       // utility parameters per lane and pass
   constexpr int LQ = 8, KQ = 4;                                        // lane = kq * 8 + lq
@@ -124,13 +124,29 @@ __global__ void __launch_bounds__(MC_NT) uei_mc_kernel(McParams p) {
   const int warp_global = blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * MC_WARPS;
   const int m = (M > 0) ? M : p.m;
+  // the next candidate's posterior is fetched while the current one is being evaluated: with one warp per candidate and four warps per
+  // scheduler the load + sqrt latency at the top of every candidate was exposed
+  double mu_n[MM], var_n[MM];
+#pragma unroll
+  for (int j = 0; j < MM; ++j)
+    if (j < m && warp_global < p.N) {
+      mu_n[j] = p.mean[(size_t)j * p.N + warp_global];
+      var_n[j] = p.var[(size_t)j * p.N + warp_global];
+    }
   for (int c = warp_global; c < p.N; c += nwarps) {
     double mu[MM], sg[MM];
 #pragma unroll
     for (int j = 0; j < MM; ++j)
       if (j < m) {
-        mu[j] = p.mean[(size_t)j * p.N + c];
-        sg[j] = sqrt(p.var[(size_t)j * p.N + c]);
+        mu[j] = mu_n[j];
+        sg[j] = sqrt(var_n[j]);
+      }
+    const int cn = c + nwarps;
+#pragma unroll
+    for (int j = 0; j < MM; ++j)
+      if (j < m && cn < p.N) {
+        mu_n[j] = p.mean[(size_t)j * p.N + cn];
+        var_n[j] = p.var[(size_t)j * p.N + cn];
       }
     double acc = 0.0;
     for (int l0 = 0; l0 < p.Lt; l0 += LQ * TL) {

@@ -682,3 +682,15 @@ def test_mixed_kernels_per_attribute_and_non_ard():
     check_close(gm.posterior_mean_gradient(Xc[:50]), om.posterior_mean_gradient(Xc[:50]), "mixed kernels dmean")
     check_dvar(gm.posterior_variance_gradient(Xc[:50]), om, Xc[:50], "mixed kernels dvar")
     check_close(gm.predict(Xc[:7])[1], om.predict(Xc[:7])[1], "small path var", rtol=1e-8)
+
+
+def test_int8_peak_probe_reports_a_plausible_rate():
+    """`bopl_probe_int8_peak` (bench.py's roofline denominator): back-to-back tcgen05.mma kind::i8 on every SM — a B200 sustains between
+    2.5 and 5 POP/s depending on clocks and power; the timed launch is about as long as asked."""
+    import ctypes
+    p = make_problem("dtlz1a_linear")
+    eng = gpu_model(p).engine
+    tops, ms = ctypes.c_double(), ctypes.c_double()
+    eng._check(eng.lib.bopl_probe_int8_peak(eng.h, 50.0, ctypes.byref(tops), ctypes.byref(ms)))
+    assert 2500.0 < tops.value < 5000.0, tops.value
+    assert 10.0 < ms.value < 200.0, ms.value

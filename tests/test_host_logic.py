@@ -372,3 +372,25 @@ def test_sampling_policies_surface():
     assert np.array_equal(pol.suggest_sample(), [[1.0, 1.0, 1.0]]) and acq.updated == 1
     assert acq.optimizer.context_manager.noncontext_bounds == space.get_bounds()
     assert uTS.analytical_gradient_prediction and AcquisitionFunction.analytical_gradient_prediction
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys, the same
+    `config.workload` string the GPU arm prints, both CPU figures (vectorised port + the reference's loop form), no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--n", "150",
+                          "--cpu-sample", "256", "--loop-sample", "8"], stdout=subprocess.PIPE, universal_newlines=True, check=True, timeout=300).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in b, key
+    assert b["impl"] == "reference" and b["value"] > 0 and b["cpu_baseline"]["kind"] == "port" and b["cpu_baseline"]["cores"] >= 1
+    assert b["cpu_baseline"]["loop_form"]["value"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+    class A: n, candidates, n_w, L = 150, 2 ** 20, 64, 32
+    assert b["config"]["workload"] == bench.workload_string(bench.workload(A), "linear")
