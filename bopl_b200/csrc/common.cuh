@@ -84,7 +84,7 @@ struct bopl_handle {
   // use_ozaki = 1 (default): the update on the int8 tensor pipe (posterior_ozaki.cu), oz_digits per operand; 0: fp64 DMMA kernel
   int use_ozaki = 1;
   bool has_oz = false;
-  int oz_cluster = 1;                  // BOPL_OZ_CLUSTER=0 disables: CTA pairs sharing the factor's digit images by multicast (posterior_ozaki.cu)
+  int oz_cluster = 1;                  // BOPL_OZ_CLUSTER: 1 (default) row-paired CTA clusters where they are the faster launch form, 2 always, 0 never (posterior_ozaki.cu)
   int oz_digits = 7;                   // digits of the model's images (fixed at upload): 7 = 55 fractional bits (default), 6 = 47
   void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem[3] = {0, 0, 0};
   size_t hsmall_cap = 0;

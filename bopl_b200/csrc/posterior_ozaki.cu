@@ -949,7 +949,18 @@ namespace {
 template <int S, int NST>
 int launch_oz_n(bopl_handle* h, OzParams& p, cudaStream_t st, size_t& attr) {
   const long long items = (long long)p.ntiles * h->m;
-  const bool rp = h->oz_cluster != 0 && h->sms >= 2;
+  // Launch form (the results are bit-identical): row-paired clusters put TWO SMs on every work item — 1.7x faster per item when there are fewer
+  // items than SM pairs (the reference's own anchor batch: 400 candidates = 12 items at m = 3), and the better form for long launches (one solved
+  // panel per pair: a quarter of the DRAM traffic, the board runs at its power limit either way).  In between, one CTA per item can need fewer
+  // rounds: a pair round costs ~1/1.65 of a single-CTA round (tools/batch_latency.py, profiles/r02_batch_latency_n2000.json).
+  bool rp = h->oz_cluster != 0 && h->sms >= 2;
+  if (rp && h->oz_cluster == 1) {
+    const long long pairs = h->sms / 2;
+    if (items > pairs && items < 8LL * h->sms) {
+      const long long r_rp = (items + pairs - 1) / pairs, r_single = (items + h->sms - 1) / h->sms;
+      if (1.65 * (double)r_single < (double)r_rp) rp = false;
+    }
+  }
   const int units = (int)std::min<long long>(items, rp ? h->sms / 2 : h->sms);      // CTA pairs or CTAs, one solved panel each
   const int grid = rp ? 2 * units : units;
   const int nb = h->n_pad / OB;

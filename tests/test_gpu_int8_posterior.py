@@ -169,21 +169,27 @@ def test_blocked_kernels_against_reference_generated_golden(fname, kernel):
     assert np.argmax(a) == np.argmax(g["acq_sequential"])
 
 
-def test_int8_cluster_pairs_equal_single_ctas_bit_for_bit(monkeypatch):
-    """The default launch runs clusters of two CTAs per candidate tile (even block rows in one, odd ones in the other, the solved panel's
-    k-steps multicast into both, partial sums combined through the peer's shared memory); the arithmetic per candidate is the same in
-    the same order, so the results equal the single-CTA launch bit for bit — several tiles per pair, ragged last tile."""
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_int8_cluster_pairs_equal_single_ctas_bit_for_bit(monkeypatch, kernel):
+    """Row-paired launch (clusters of two CTAs per candidate tile: even block rows in one, odd ones in the other, the solved panel's
+    k-steps multicast into both, partial sums combined through the peer's shared memory) against one CTA per tile: the arithmetic per
+    candidate is the same in the same order, so the results are equal bit for bit — several tiles per pair, ragged last tile — and so
+    is whatever the default picks (the launch form is chosen by the number of work items)."""
     p = make_problem("S", n=300, N=149 * 128 - 37)          # 149 tiles x 3 attributes: six work items per pair
-    monkeypatch.setenv("BOPL_OZ_CLUSTER", "1")
-    g1 = gpu_model(p, gradients=False, posterior_kernel="int8")
-    mu1, v1 = g1.predict(p["Xc"])
-    monkeypatch.setenv("BOPL_OZ_CLUSTER", "0")
-    g0 = gpu_model(p, gradients=False, posterior_kernel="int8")
-    mu0, v0 = g0.predict(p["Xc"])
-    assert np.array_equal(mu1, mu0) and np.array_equal(v1, v0)
-    g64 = gpu_model(p, gradients=False, posterior_kernel="fp64")
-    mu_d, v_d = g64.predict(p["Xc"])
-    assert scaled_err(mu1, mu_d) < 1e-12 and rel_err(v1, v_d) < 1e-10
+    res = {}
+    for mode in ("2", "0", "1"):                            # always paired / never / by item count (default)
+        monkeypatch.setenv("BOPL_OZ_CLUSTER", mode)
+        res[mode] = gpu_model(p, gradients=False, posterior_kernel=kernel).predict(p["Xc"])
+    for mode in ("0", "1"):
+        assert np.array_equal(res["2"][0], res[mode][0]) and np.array_equal(res["2"][1], res[mode][1]), mode
+    monkeypatch.delenv("BOPL_OZ_CLUSTER")
+    mu_d, v_d = gpu_model(p, gradients=False, posterior_kernel="fp64").predict(p["Xc"])
+    assert scaled_err(res["2"][0], mu_d) < 1e-12 and rel_err(res["2"][1], v_d) < (1e-10 if kernel == "int8" else 1e-12)
+    # a small batch (fewer work items than SM pairs: paired by default) and a mid-size one (one CTA per item needs fewer rounds)
+    gm = gpu_model(p, gradients=False, posterior_kernel=kernel)
+    for N in (400, 4096):
+        mu, v = gm.predict(p["Xc"][:N])
+        assert np.array_equal(mu, res["2"][0][:, :N]) and np.array_equal(v, res["2"][1][:, :N])
 
 
 def test_int8_posterior_many_block_rows():
