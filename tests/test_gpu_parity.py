@@ -694,3 +694,29 @@ def test_int8_peak_probe_reports_a_plausible_rate():
     eng._check(eng.lib.bopl_probe_int8_peak(eng.h, 50.0, ctypes.byref(tops), ctypes.byref(ms)))
     assert 2500.0 < tops.value < 5000.0, tops.value
     assert 10.0 < ms.value < 200.0, ms.value
+
+
+def test_calls_on_different_streams_are_ordered_by_the_library():
+    """The handle's scratch (mean / variance, solved panels, top-k levels) is shared by every entry point; a device-tensor call on a
+    caller's side stream followed by a host-buffer call (which runs on the library's own stream), and the reverse, must give the same
+    numbers as the same calls on one stream (api.cu: StreamOrder — the later stream waits for an event behind the earlier call)."""
+    import torch
+    p = make_problem("S", n=300, N=6000, n_w=16, L=8)
+    gm = gpu_model(p, gradients=False)
+    acq = gpu_acquisition(p, gm)
+    eng = gm.engine
+    want_a = acq._compute_acq(p["Xc"])[:, 0]
+    Xd = eng.to_dev(p["Xc"])
+    mu0, v0 = eng.posterior_dev(Xd, 0)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=eng.device)
+    for _ in range(5):
+        with torch.cuda.stream(side):
+            mu, v = eng.posterior_dev(Xd, 0)                     # async on the side stream, uses the handle's panel scratch
+        a = acq._compute_acq(p["Xc"])[:, 0]                      # host-buffer call on the library's stream, right behind it
+        with torch.cuda.stream(side):
+            mu2, v2 = eng.posterior_dev(Xd[:3000], 0)
+        side.synchronize()
+        assert np.array_equal(a, want_a)
+        assert torch.equal(mu, mu0) and torch.equal(v, v0)
+        assert torch.equal(mu2, mu0[:, :3000]) and torch.equal(v2, v0[:, :3000])

@@ -156,3 +156,28 @@ def test_nccl_allgather_of_real_ranks_equals_whole_batch_topk(tmp_path):
             assert np.array_equal(g["v" + tag], val_w), (r, tag)
             assert np.array_equal(g["x" + tag], X[idx_w]), (r, tag)
         assert np.array_equal(g["is_"], is_w) and np.array_equal(g["vs"], vs_w) and np.array_equal(g["xs"], X[is_w])
+
+
+def test_collective_entry_points_reject_bad_arguments():
+    """Error behaviour of the multi-GPU entry points: status codes + message, no exception across the ABI, nothing launched."""
+    import torch
+    from bopl_b200._lib import BoplError
+    p = make_problem("dtlz1a_linear", N=50)
+    eng = gpu_model(p, gradients=False).engine
+    v, i = eng.empty(5), torch.zeros(5, dtype=torch.int64, device=eng.device)
+    Xd = eng.to_dev(p["Xc"])
+    out_v, out_i = eng.empty(5), torch.zeros(5, dtype=torch.int64, device=eng.device)
+    with pytest.raises(BoplError) as ei:          # no communicator
+        eng._check(eng.lib.bopl_topk_allgather(eng.h, None, v.data_ptr(), i.data_ptr(), 5, Xd.data_ptr(), 0, 5, out_v.data_ptr(), out_i.data_ptr(), None,
+                                               eng._stream()))
+    assert ei.value.code == -1 and "communicator" in str(ei.value)
+    rec = eng.empty(5, 2 + p["d"])
+    for k_local, k in ((6, 5), (-1, 5), (1, 0), (1, 300)):
+        with pytest.raises(BoplError):
+            eng._check(eng.lib.bopl_topk_pack(eng.h, v.data_ptr(), i.data_ptr(), k_local, Xd.data_ptr(), 0, k, rec.data_ptr(), eng._stream()))
+    with pytest.raises(BoplError):
+        eng._check(eng.lib.bopl_topk_merge(eng.h, None, 5, 5, out_v.data_ptr(), out_i.data_ptr(), None, eng._stream()))
+    with pytest.raises(BoplError):                # rank outside the communicator
+        comm = ctypes.c_void_p()
+        ident = np.zeros(128, dtype=np.uint8)
+        eng._check(eng.lib.bopl_nccl_comm_init(eng.h, 2, 2, ctypes.c_void_p(ident.ctypes.data), ctypes.byref(comm)))
