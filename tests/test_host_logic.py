@@ -394,3 +394,17 @@ def test_bench_reference_arm_prints_one_contract_line():
     import bench
     class A: n, candidates, n_w, L = 150, 2 ** 20, 64, 32
     assert b["config"]["workload"] == bench.workload_string(bench.workload(A), "linear")
+
+
+def test_c_abi_header_is_plain_c99(tmp_path):
+    """include/bopl_b200.h is the drop-in boundary: it must compile as C (no C++ or torch types in any signature)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "bopl_b200.h"\nint main(void) { bopl_handle* h = 0; return bopl_create(&h, 0) == 0 ? 0 : 1; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                          str(tmp_path / "hdr.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    assert res.returncode == 0, res.stdout
