@@ -499,9 +499,13 @@ def run_extras(args, torch, dev, local_rank, p, state, model, Xd, flush, rooflin
     for kind in ("int8x7", "fp64", "int8"):
         if kind not in models:
             models[kind] = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel=kind)
-    os.environ["BOPL_OZ_CLUSTER"] = "0"
+    saved = os.environ.get("BOPL_OZ_CLUSTER")
+    os.environ["BOPL_OZ_CLUSTER"] = "0"                   # read by bopl_create
     models["int8x7_single_cta"] = MultiOutputGP.from_state(state, device=local_rank, posterior_kernel="int8x7")
-    del os.environ["BOPL_OZ_CLUSTER"]
+    if saved is None:
+        del os.environ["BOPL_OZ_CLUSTER"]
+    else:
+        os.environ["BOPL_OZ_CLUSTER"] = saved
     kernels, var64 = {}, None
     for kind in ("fp64", "int8x7", "int8", "int8x7_single_cta"):
         eng = models[kind].engine
