@@ -60,6 +60,13 @@ int dev_upload(bopl_handle* h, const T* src, size_t count, T** out) {
   return BOPL_OK;
 }
 
+// Value + gradient entry points: the small-batch posterior and its gradient share one K* / dK generation (gp_kernels.cu).
+struct GradFollows {
+  bopl_handle* h;
+  GradFollows(bopl_handle* h_, bool on) : h(h_) { h->small_grad_follows = on; }
+  ~GradFollows() { h->small_grad_follows = false; }
+};
+
 int uploads_done(bopl_handle* h) {
   BOPL_CUDA(h, cudaDeviceSynchronize());
   return BOPL_OK;
@@ -508,6 +515,7 @@ int bopl_uei_grad(bopl_handle* h, const double* Xc, int N, const double* Z, int 
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_mv(h, (size_t)h->m * N)) || (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
   const double scale = 1.0 / ((double)nH * (double)nw);
+  GradFollows fuse(h, true);
   for (int hh = 0; hh < nH; ++hh) {
     if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
     if ((rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
@@ -549,6 +557,7 @@ int bopl_uei_grad_host(bopl_handle* h, const double* Xc_h, int N, const double* 
   BOPL_CUDA(h, cudaMemcpyAsync(bd, best_h, nB * sizeof(double), cudaMemcpyHostToDevice, st));
   if ((rc = ensure_mv(h, (size_t)h->m * N)) || (rc = ensure_grad(h, (size_t)h->m * N * d))) return rc;
   const double scale = 1.0 / ((double)nH * (double)nw);
+  GradFollows fuse(h, true);
   for (int hh = 0; hh < nH; ++hh) {
     if ((rc = launch_posterior_trsm(h, Xd, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
     if ((rc = launch_posterior_grad(h, Xd, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
@@ -578,6 +587,7 @@ int bopl_expected_utility(bopl_handle* h, const double* Xc, int N, const double*
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
   if (dval && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
+  GradFollows fuse(h, dval != nullptr);
   for (int hh = 0; hh < nH; ++hh) {
     // predict_noiseless: no likelihood variance, clipped at 1e-10 (gpmodel.py:181-190)
     if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_CLIP, st))) return rc;
@@ -608,6 +618,7 @@ int bopl_uei_affine(bopl_handle* h, const double* Xc, int N, const double* theta
   if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
   if (dacq && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
   const double scale = 1.0 / (double)nH;
+  GradFollows fuse(h, dacq != nullptr);
   for (int hh = 0; hh < nH; ++hh) {
     if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
     if (dacq && (rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;
@@ -633,6 +644,7 @@ int bopl_uei_constrained(bopl_handle* h, const double* Xc, int N, const double* 
   if ((rc = ensure_mv(h, (size_t)h->m * N))) return rc;
   if (dacq && (rc = ensure_grad(h, (size_t)h->m * N * h->d))) return rc;
   const double scale = 1.0 / (double)nH;
+  GradFollows fuse(h, dacq != nullptr);
   for (int hh = 0; hh < nH; ++hh) {
     if ((rc = launch_posterior_trsm(h, Xc, N, hh, h->mean_s, h->var_s, BOPL_VAR_INCLUDE_NOISE | BOPL_VAR_CLIP, st))) return rc;
     if (dacq && (rc = launch_posterior_grad(h, Xc, N, hh, h->dmean_s, h->dvar_s, st))) return rc;

@@ -46,6 +46,7 @@ struct bopl_handle {
   int n_pad = 0, pad = 0;
   bool has_model = false, has_winv = false, has_linv = false;
   int small_path = 1;                  // BOPL_SMALL_PATH=0 forces the blocked TRSM kernel for every batch size
+  bool small_grad_follows = false;     // set by the value+gradient entry points around their posterior + posterior-gradient pair (small-batch path)
   double* small_scratch = nullptr; size_t small_scratch_bytes = 0;
   std::string err;
   long long launches = 0;

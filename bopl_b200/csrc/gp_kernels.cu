@@ -321,59 +321,85 @@ __global__ void __launch_bounds__(256) small_kstar_kernel(SmallParams p) {
 }
 
 // out[j][c][i] = scale * sum_k M_j[i][k] K[j][c][k];  TRI: M = Linv (k <= i), scale 1;  else M = Winv, scale -2.
-// Block = 8 warps = 8 consecutive rows i of M; the K* rows of ALL candidates go through shared memory in k-tiles of 128,
-// so M is streamed once whatever the batch size, with four independent 256-byte loads per warp and tile in flight.
-// Each (candidate, row) sum runs over k in a fixed order (lane-strided, tiles ascending, xor-shuffle tree) that does
-// not depend on the other candidates in the batch.
-constexpr int GV_KT = 128;
-template <bool TRI, int NC>
-__global__ void __launch_bounds__(256) small_gemv_kernel(SmallParams p) {
-  __shared__ double Ks[NC][GV_KT];
+// A skinny matrix product on DMMA.8x8x4, bound by streaming M once (32 MB per attribute at n = 2000): CTA = 32 rows of M x up to 32
+// candidates, four warps of 8 rows each; 32-deep k-tiles of M (coalesced 8-byte cp.async, zero-filled past n) and of the candidates' K* rows
+// go through a double-buffered shared-memory ring; fragments are read with a 36-double row pitch (two wavefronts per 8-byte warp load, the
+// minimum).  Per (candidate, row) the k order is fixed and does not depend on the other candidates: bit-identical alone or in a batch.
+// Round 1's form (a warp per row, K* through shared memory for every FMA: one 8-byte shared load per fp64 operation) took 184 + 286 us for
+// the two products of a 20-anchor L-BFGS step at n = 2000 — 15x the time the 144 MB of factors need to stream.
+constexpr int GV_ROWS = 32, GV_KT = 32, GV_PITCH = 36, GV_NT = 128;
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes));
+}
+
+template <bool TRI, int NT>      // NT tiles of 8 candidates
+__global__ void __launch_bounds__(GV_NT) small_gemv_kernel(SmallParams p) {
+  constexpr int NC = 8 * NT;
+  __shared__ __align__(16) double Ms[2][GV_ROWS][GV_PITCH];
+  __shared__ __align__(16) double Ks[2][NC][GV_PITCH];
   const int j = blockIdx.y;
   const GpDev& gp = p.gps[j * p.H + p.hsel];
-  const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * 8, i = i0 + warp;
+  const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int i0 = blockIdx.x * GV_ROWS;
   const double* M = TRI ? gp.Linv : gp.Winv;
-  const double* Mrow = M + (size_t)min(i, n - 1) * n;
-  const int kend = TRI ? min(i0 + 8, n) : n;          // the block's last row bounds the k-range of a triangular factor
   const double* Kj = p.K + (size_t)j * p.N * n;
-  double acc[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-  for (int k0 = 0; k0 < kend; k0 += GV_KT) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < NC * GV_KT; idx += 256) {
+  const int kend = TRI ? min(i0 + GV_ROWS, n) : n;          // the block's last row bounds the k-range of a triangular factor
+  const int ntiles = (kend + GV_KT - 1) / GV_KT;
+  auto issue = [&](int tile) {
+    const int k0 = tile * GV_KT, buf = tile & 1;
+    for (int idx = tid; idx < GV_ROWS * GV_KT; idx += GV_NT) {
+      const int r = idx / GV_KT, kk = idx - r * GV_KT;
+      const bool ok = (i0 + r < n) && (k0 + kk < n);
+      cp_async8_zfill(&Ms[buf][r][kk], M + (size_t)min(i0 + r, n - 1) * n + min(k0 + kk, n - 1), ok);
+    }
+    for (int idx = tid; idx < NC * GV_KT; idx += GV_NT) {
       const int c = idx / GV_KT, kk = idx - c * GV_KT;
-      Ks[c][kk] = (c < p.N && k0 + kk < n) ? Kj[(size_t)c * n + k0 + kk] : 0.0;
+      const bool ok = (c < p.N) && (k0 + kk < n);
+      cp_async8_zfill(&Ks[buf][c][kk], Kj + (size_t)min(c, p.N - 1) * n + min(k0 + kk, n - 1), ok);
     }
+  };
+  double acc[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  const int row = i0 + 8 * warp + g;                        // this lane's row of M in the A fragments
+  issue(0);
+  cp_async_commit();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    if (tile + 1 < ntiles) issue(tile + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    double mv[GV_KT / 32];
+    const int buf = tile & 1, k0 = tile * GV_KT;
 #pragma unroll
-    for (int u = 0; u < GV_KT / 32; ++u) {
-      const int k = k0 + lane + 32 * u;
-      mv[u] = (k < n && (!TRI || k <= i)) ? Mrow[k] : 0.0;
+    for (int kk = 0; kk < GV_KT; kk += 4) {
+      double a = Ms[buf][8 * warp + g][kk + t];
+      if (TRI && k0 + kk + t > row) a = 0.0;               // the strictly upper part of a triangular factor is never used, whatever it holds
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dmma(acc[nt][0], acc[nt][1], a, Ks[buf][8 * nt + g][kk + t]);
     }
-#pragma unroll
-    for (int u = 0; u < GV_KT / 32; ++u)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = fma(mv[u], Ks[c][lane + 32 * u], acc[c]);
+    __syncthreads();                                        // the buffer is refilled two tiles later: every warp must be done with it
   }
   double* out = (TRI ? p.V : p.B) + (size_t)j * p.N * n;
+  const double scale = TRI ? 1.0 : -2.0;
+  if (row < n) {
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    double v = acc[c];
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && c < p.N && i < n) out[(size_t)c * n + i] = (TRI ? 1.0 : -2.0) * v;
+      for (int e = 0; e < 2; ++e) {
+        const int c = 8 * nt + 2 * t + e;
+        if (c < p.N) out[(size_t)c * n + row] = scale * acc[nt][e];
+      }
   }
 }
 
 template <bool TRI>
 void launch_small_gemv(const SmallParams& p, int n, int m, cudaStream_t st) {
-  dim3 grid((n + 7) / 8, m);
-  if (p.N <= 8) small_gemv_kernel<TRI, 8><<<grid, 256, 0, st>>>(p);
-  else if (p.N <= 16) small_gemv_kernel<TRI, 16><<<grid, 256, 0, st>>>(p);
-  else small_gemv_kernel<TRI, 32><<<grid, 256, 0, st>>>(p);
+  dim3 grid((n + GV_ROWS - 1) / GV_ROWS, m);
+  if (p.N <= 8) small_gemv_kernel<TRI, 1><<<grid, GV_NT, 0, st>>>(p);
+  else if (p.N <= 16) small_gemv_kernel<TRI, 2><<<grid, GV_NT, 0, st>>>(p);
+  else small_gemv_kernel<TRI, 4><<<grid, GV_NT, 0, st>>>(p);
 }
 
 // mean = K* alpha + ymean, var = variance - sum V^2 (+noise, clip).  One block per (candidate, attribute), fixed order.
@@ -548,7 +574,9 @@ int launch_posterior_small(bopl_handle* h, const double* Xc, int N, int hsel, do
   p.mean = mean;
   p.var = var;
   p.flags = flags;
-  small_kstar_kernel<false><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
+  // value + gradient entry points (small_grad_follows): K* and (dK/dr)/r are generated once, the gradient half of the call reuses them
+  if (h->small_grad_follows) small_kstar_kernel<true><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
+  else small_kstar_kernel<false><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
   BOPL_LAUNCH_CHECK(h, "small_kstar_kernel");
   if (var) {
     launch_small_gemv<true>(p, h->n, h->m, st);
@@ -580,8 +608,10 @@ static int launch_posterior_grad_small(bopl_handle* h, const double* Xc, int N, 
   if (rc) return rc;
   p.dmean = dmean;
   p.dvar = dvar;
-  small_kstar_kernel<true><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
-  BOPL_LAUNCH_CHECK(h, "small_kstar_kernel<G>");
+  if (!h->small_grad_follows) {        // standalone gradient call: nothing has generated K*, G for these candidates
+    small_kstar_kernel<true><<<dim3((h->n + 255) / 256, h->m), 256, 0, st>>>(p);
+    BOPL_LAUNCH_CHECK(h, "small_kstar_kernel<G>");
+  }
   if (dvar) {
     launch_small_gemv<false>(p, h->n, h->m, st);
     BOPL_LAUNCH_CHECK(h, "small_gemv_kernel<Winv>");
