@@ -260,3 +260,48 @@ def test_int8_full_size_config_S(kernel):
     val64, idx64, a64 = gpu_acquisition(p, g64).top_candidates(p["Xc"], 20, want_acq=True)
     assert np.array_equal(idx, idx64)
     assert scaled_err(a, a64) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_int8x7_randomised_shapes_against_fp64_kernel_and_oracle(seed):
+    """Random (n, d, m, N, kernel kind, launch form) draws for the default posterior kernel: mean and variance of BOTH full-precision
+    kernels against the oracle under the usual bounds, and against each other.  Exercises odd tile counts, several work items per CTA
+    pair, 2 ... 20 block rows, wide inputs, badly conditioned models and both launch forms."""
+    import os
+    from bopl_b200.models import MultiOutputGP, state_from_hyperparameters
+    rs = np.random.RandomState(100 + seed)
+    n = int(rs.choice([70, 130, 200, 333, 520, 777, 1100, 1290]))
+    d = int(rs.choice([1, 3, 7, 12, 13, 24]))
+    m = int(rs.choice([1, 2, 5]))
+    N = int(rs.choice([33, 129, 500, 1537, 4000, 9001]))
+    kind = str(rs.choice(["Mat52", "rbf", "Mat32", "ExpQuad"]))
+    mode = str(rs.choice(["0", "1", "2"]))
+    X, Xc = rs.uniform(size=(n, d)), rs.uniform(size=(N, d))
+    Y = np.stack([np.sin(X @ rs.normal(size=d)) + 0.1 * rs.normal(size=n) for _ in range(m)])
+    ell = rs.uniform(0.4, 1.2, size=(m, 1, d)) * np.sqrt(d)
+    var = rs.uniform(0.5, 2.0, size=(m, 1))
+    st = state_from_hyperparameters(X, Y, [kind] * m, var, ell, np.full((m, 1), 1e-4), want_winv=False)
+    os.environ["BOPL_OZ_CLUSTER"] = mode
+    try:
+        a = MultiOutputGP.from_state(st, posterior_kernel="int8x7")
+    finally:
+        del os.environ["BOPL_OZ_CLUSTER"]
+    b = MultiOutputGP.from_state(st, posterior_kernel="fp64")
+    assert a.engine.posterior_kernel == "int8x7"
+    mu_a, v_a = a.predict(Xc)
+    mu_b, v_b = b.predict(Xc)
+    what = "seed %d: n=%d d=%d m=%d N=%d %s mode %s" % (seed, n, d, m, N, kind, mode)
+    # both kernels against the oracle under the usual bounds (the draws include badly conditioned models — one input dimension, 1000+
+    # points — where two fp64 summation orders of K* alpha already differ by 1e-10 of the scale), and against each other within the same
+    p = dict(X=X, Y=Y, kinds=[kind] * m, variance=var, lengthscale=ell, noise=np.full((m, 1), 1e-4), H=1, m=m)
+    om = oracle_model(p)
+    mu_o, v_o = om.predict(Xc)
+    floor = variance_floor(om, Xc)
+    bound = RTOL * np.abs(v_o) + 64 * floor + 1e-300
+    check_close(mu_a, mu_o, what + " mean (int8x7)")
+    check_close(mu_b, mu_o, what + " mean (fp64)")
+    assert np.all(np.abs(v_a - v_o) <= bound), (what, float(np.max(np.abs(v_a - v_o) / bound)))
+    assert np.all(np.abs(v_b - v_o) <= bound), (what, float(np.max(np.abs(v_b - v_o) / bound)))
+    assert np.all(np.abs(v_a - v_b) <= bound), (what, float(np.max(np.abs(v_a - v_b) / bound)))
+    print("%s: worst |dv| / bound: int8x7 %.3f, fp64 %.3f, int8x7 vs fp64 %.3f; mean int8x7 vs fp64 %.2e of scale"
+          % (what, np.max(np.abs(v_a - v_o) / bound), np.max(np.abs(v_b - v_o) / bound), np.max(np.abs(v_a - v_b) / bound), scaled_err(mu_a, mu_b)))
