@@ -626,8 +626,22 @@ int launch_posterior_grad(bopl_handle* h, const double* Xc, int N, int hsel, dou
   if (N <= 0) return BOPL_OK;
   if (use_small_path(h, N)) return launch_posterior_grad_small(h, Xc, N, hsel, dmean, dvar, st);
   const int n = h->n, d = h->d;
-  const int chunk = 2048;                                          // whole 128-row tiles of the beta GEMM
   const int ldk = (n + GM_BK - 1) / GM_BK * GM_BK, wrows = (n + GM_BN - 1) / GM_BN * GM_BN;
+  // candidates per pass: whole 128-row tiles of the beta GEMM, and a tile count that makes the GEMM grid (row tiles x column tiles) a whole
+  // number of waves of one CTA per SM (n = 2000 on 148 SMs: 37 x 16 = 592 CTAs = 4 waves; 16 x 16 = 256 was 1.73)
+  int row_tiles = 16;
+  {
+    const int ctiles = wrows / GM_BN;
+    int a = h->sms, b = ctiles;
+    while (b) {
+      const int t = a % b;
+      a = b;
+      b = t;
+    }
+    const int rt = h->sms / a;
+    if (rt * GM_BM <= 8192) row_tiles = rt;
+  }
+  const int chunk = std::min(row_tiles * GM_BM, (N + GM_BM - 1) / GM_BM * GM_BM);      // never more rows than the batch has (whole tiles)
   const size_t kb_cnt = (size_t)chunk * ldk, gb_cnt = (size_t)chunk * n, wp_cnt = dvar ? (size_t)wrows * ldk : 0;
   size_t need = (kb_cnt + 2 * gb_cnt + wp_cnt) * sizeof(double);
   int rc = ensure_bytes(h, (void**)&h->grad_scratch, &h->grad_scratch_bytes, need);
