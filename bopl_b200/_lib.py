@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 KERNEL_KINDS = {"Mat52": 0, "rbf": 1, "Mat32": 2, "ExpQuad": 3}
 UTILITY_KINDS = {"linear": 0, "quadratic": 1, "exponential": 2, "constrained": 3}
-POSTERIOR_KERNELS = {"fp64": 0, "int8": 6, "int8x7": 7}   # bopl_set_posterior_kernel; the library default is int8x7
+POSTERIOR_KERNELS = {"fp64": 0, "int8": 6, "int8x7": 7, "int8auto": 60}   # bopl_set_posterior_kernel; the library default is int8x7
 VAR_INCLUDE_NOISE = 1
 VAR_CLIP = 2
 ERR_NUMERIC = -5

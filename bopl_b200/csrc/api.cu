@@ -67,6 +67,48 @@ struct GradFollows {
   ~GradFollows() { h->small_grad_follows = false; }
 };
 
+// BOPL_POSTERIOR_INT8_AUTO: does the 6-digit split meet the path's bound for THIS model?  The worst place for an absolute error is where
+// the variance is smallest — at the training points — so the probe runs (up to) 256 of them through the 6-digit kernel and through the fp64
+// DMMA kernel (noiseless variance, no clip, every hyper-sample) and asks for |v6 - v64| <= 1e-9 |v64| + 64 ulp(sigma^2) on every one.
+// Returns 1 (keep 6 digits), 0 (use 7), or a negative status.
+int int8_probe_passes(bopl_handle* h) {
+  const int n = h->n, d = h->d, m = h->m;
+  const int N = std::max(SMALL_N + 1, std::min(n, 256));
+  std::vector<double> Xh((size_t)n * d), Xp((size_t)N * d);
+  BOPL_CUDA(h, cudaMemcpy(Xh.data(), h->X_dev, Xh.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < N; ++c) {
+    const int i = (int)(((long long)c * n) / N) % n;                 // spread over the training set (repeats when n < 33)
+    memcpy(Xp.data() + (size_t)c * d, Xh.data() + (size_t)i * d, (size_t)d * sizeof(double));
+  }
+  double* buf = nullptr;
+  BOPL_CUDA(h, cudaMalloc((void**)&buf, ((size_t)N * d + 2 * (size_t)m * N) * sizeof(double)));
+  double *Xd = buf, *v6 = buf + (size_t)N * d, *v64 = v6 + (size_t)m * N;
+  std::vector<double> a((size_t)m * N), b((size_t)m * N);
+  int ok = 1, rc = BOPL_OK;
+  cudaStream_t st = h->s_compute;
+  cudaError_t e = cudaMemcpy(Xd, Xp.data(), Xp.size() * sizeof(double), cudaMemcpyHostToDevice);
+  for (int hh = 0; hh < h->H && ok == 1 && e == cudaSuccess && rc == BOPL_OK; ++hh) {
+    if ((rc = launch_posterior_ozaki(h, Xd, N, hh, nullptr, v6, 0, st)) || (rc = launch_posterior_trsm_t(h, Xd, N, hh, nullptr, v64, 0, st))) break;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(a.data(), v6, a.size() * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(b.data(), v64, b.size() * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    for (int j = 0; j < m && ok == 1; ++j) {
+      const double s2 = h->gp_host[(size_t)j * h->H + hh].variance;
+      for (int c = 0; c < N; ++c) {
+        const double x = a[(size_t)j * N + c], y = b[(size_t)j * N + c];
+        if (!(std::fabs(x - y) <= 1e-9 * std::fabs(y) + 64.0 * 2.220446049250313e-16 * s2)) {
+          ok = 0;
+          break;
+        }
+      }
+    }
+  }
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, BOPL_ERR_CUDA, std::string("int8 probe: ") + cudaGetErrorString(e));
+  return ok;
+}
+
 int uploads_done(bopl_handle* h) {
   BOPL_CUDA(h, cudaDeviceSynchronize());
   return BOPL_OK;
@@ -172,14 +214,15 @@ int bopl_create(bopl_handle** out, int device) {
   if (const char* v = getenv("BOPL_OZ_CLUSTER")) h->oz_cluster = atoi(v);
   if (const char* v = getenv("BOPL_POSTERIOR")) {        // "int8x7" (default), "int8" (6 digits), "fp64"
     const std::string k(v);
-    if (k == "int8" || k == "int8x7") {
+    if (k == "int8" || k == "int8x7" || k == "int8auto") {
       h->use_ozaki = 1;
-      h->oz_digits = k == "int8" ? 6 : 7;
+      h->oz_digits = k == "int8x7" ? 7 : 6;
+      h->oz_auto = k == "int8auto";
     } else if (k == "fp64") {
       h->use_ozaki = 0;
     } else {
       delete h;
-      return fail(nullptr, BOPL_ERR_INVALID, "BOPL_POSTERIOR must be int8x7, int8 or fp64");
+      return fail(nullptr, BOPL_ERR_INVALID, "BOPL_POSTERIOR must be int8x7, int8, int8auto or fp64");
     }
   }
   if (const char* v = getenv("BOPL_TRSM_STAGES")) h->trsm_stages = atoi(v);
@@ -228,8 +271,16 @@ long long bopl_launch_count(const bopl_handle* h) { return h ? h->launches : 0; 
 
 int bopl_set_posterior_kernel(bopl_handle* h, int kind) {
   if (!h) return fail(nullptr, BOPL_ERR_INVALID, "null handle");
+  if (kind == BOPL_POSTERIOR_INT8_AUTO) {       // 6 digits where an upload-time probe of the model allows it, else 7: decided per model
+    if (h->has_model) return fail(h, BOPL_ERR_STATE, "select BOPL_POSTERIOR_INT8_AUTO before bopl_set_model / bopl_fit_model: the choice is made at upload");
+    h->use_ozaki = 1;
+    h->oz_digits = 6;
+    h->oz_auto = true;
+    return BOPL_OK;
+  }
   if (kind != BOPL_POSTERIOR_FP64 && kind != BOPL_POSTERIOR_INT8 && kind != BOPL_POSTERIOR_INT8_7)
     return fail(h, BOPL_ERR_INVALID, "unknown posterior kernel kind");
+  h->oz_auto = false;
   if (kind != BOPL_POSTERIOR_FP64 && h->has_model && ozaki_covers(h->d, h->n_pad) && (!h->has_oz || h->oz_digits != kind))
     return fail(h, BOPL_ERR_STATE, "the loaded model carries no digit images of that width: select the kernel before bopl_set_model / bopl_fit_model");
   if (kind == BOPL_POSTERIOR_FP64) {
@@ -246,9 +297,9 @@ int bopl_get_posterior_kernel(const bopl_handle* h) {
   return h->use_ozaki ? h->oz_digits : BOPL_POSTERIOR_FP64;
 }
 
-int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
-                   const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
-                   const double* L_h, const double* alpha_h, const double* Winv_h, const double* Linv_h) {
+static int set_model_impl(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                          const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
+                          const double* L_h, const double* alpha_h, const double* Winv_h, const double* Linv_h) {
   BOPL_CHECK_HANDLE(h);
   if (n <= 0 || d <= 0 || m <= 0 || H <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, m, H must be positive");
   if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
@@ -718,9 +769,9 @@ int bopl_uei_host(bopl_handle* h, const double* Xc_h, int N, const double* Z_h, 
 }
 
 // ---- model fit on the device (fit_kernels.cu) ---------------------------------------------------------------------------
-int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
-                   const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
-                   const double* jitter_h, int want_winv, int want_linv, double* logdet_h) {
+static int fit_model_impl(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                          const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
+                          const double* jitter_h, int want_winv, int want_linv, double* logdet_h) {
   BOPL_CHECK_HANDLE(h);
   if (n <= 0 || d <= 0 || m <= 0 || H <= 0) return fail(h, BOPL_ERR_INVALID, "n, d, m, H must be positive");
   if (d > MAX_D) return fail(h, BOPL_ERR_UNSUPPORTED, "d > 24 input dimensions");
@@ -873,6 +924,48 @@ int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_k
   h->has_model = true;
   h->F_valid = false;
   return BOPL_OK;
+}
+
+// BOPL_POSTERIOR_INT8_AUTO: upload with 6 digits, probe at the training points, upload again with 7 when the probe fails.
+static int int8_auto_keeps_six(bopl_handle* h, int rc) {
+  if (rc != BOPL_OK || !h->oz_auto || !h->has_oz || h->oz_digits != 6) return 1;
+  return int8_probe_passes(h);
+}
+
+int bopl_set_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* ell_h, const double* var_h, const double* noise_h, const double* ymean_h,
+                   const double* L_h, const double* alpha_h, const double* Winv_h, const double* Linv_h) {
+  if (h && h->oz_auto) h->oz_digits = 6;
+  int rc = set_model_impl(h, n, d, m, H, kern_kind_h, X_h, ell_h, var_h, noise_h, ymean_h, L_h, alpha_h, Winv_h, Linv_h);
+  if (rc != BOPL_OK) return rc;
+  const int keep = int8_auto_keeps_six(h, rc);
+  if (keep < 0) {
+    free_model(h);
+    return keep;
+  }
+  if (keep == 0) {
+    h->oz_digits = 7;
+    rc = set_model_impl(h, n, d, m, H, kern_kind_h, X_h, ell_h, var_h, noise_h, ymean_h, L_h, alpha_h, Winv_h, Linv_h);
+  }
+  return rc;
+}
+
+int bopl_fit_model(bopl_handle* h, int n, int d, int m, int H, const int* kern_kind_h, const double* X_h,
+                   const double* Y_h, const double* ell_h, const double* var_h, const double* noise_h,
+                   const double* jitter_h, int want_winv, int want_linv, double* logdet_h) {
+  if (h && h->oz_auto) h->oz_digits = 6;
+  int rc = fit_model_impl(h, n, d, m, H, kern_kind_h, X_h, Y_h, ell_h, var_h, noise_h, jitter_h, want_winv, want_linv, logdet_h);
+  if (rc != BOPL_OK) return rc;
+  const int keep = int8_auto_keeps_six(h, rc);
+  if (keep < 0) {
+    free_model(h);
+    return keep;
+  }
+  if (keep == 0) {
+    h->oz_digits = 7;
+    rc = fit_model_impl(h, n, d, m, H, kern_kind_h, X_h, Y_h, ell_h, var_h, noise_h, jitter_h, want_winv, want_linv, logdet_h);
+  }
+  return rc;
 }
 
 int bopl_fit_info(const bopl_handle* h, int count, int* info_h) {

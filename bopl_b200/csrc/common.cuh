@@ -87,6 +87,7 @@ struct bopl_handle {
   bool has_oz = false;
   int oz_cluster = 1;                  // BOPL_OZ_CLUSTER: 1 (default) row-paired CTA clusters where they are the faster launch form, 2 always, 0 never (posterior_ozaki.cu)
   int oz_digits = 7;                   // digits of the model's images (fixed at upload): 7 = 55 fractional bits (default), 6 = 47
+  bool oz_auto = false;                // BOPL_POSTERIOR_INT8_AUTO: 6 digits when the upload-time probe of the model passes, else 7
   void* oz_scratch = nullptr; size_t oz_scratch_bytes = 0; size_t oz_attr_smem[3] = {0, 0, 0};
   size_t hsmall_cap = 0;
 };

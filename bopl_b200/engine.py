@@ -98,8 +98,9 @@ class Engine(object):
 
     # ------------------------------------------------------------------ model
     def set_posterior_kernel(self, kind):
-        """'int8x7' (update on the int8 tensor pipe, 7-digit = 55-bit exact split; default), 'fp64' (DMMA blocked solve) or
-        'int8' (6-digit split: opt-in reduced precision).
+        """'int8x7' (update on the int8 tensor pipe, 7-digit = 55-bit exact split; default), 'fp64' (DMMA blocked solve),
+        'int8' (6-digit split: opt-in reduced precision) or 'int8auto' (6 digits when an upload-time probe of the model at its training
+        points meets 1e-9 relative on the variance, else 7; `posterior_kernel` then reports what the loaded model runs).
         Select before the model is uploaded / fitted: the digit images of the factor are built then (`bopl_set_posterior_kernel`)."""
         self._check(self.lib.bopl_set_posterior_kernel(self.h, _lib.POSTERIOR_KERNELS[kind]))
 

@@ -73,11 +73,16 @@ const char* bopl_build_info(void);
  *   BOPL_POSTERIOR_FP64   fp64 DMMA.8x8x4 blocked triangular solve (posterior_trsm_t.cu), 0.95 of the cuBLAS DGEMM peak.
  *   BOPL_POSTERIOR_INT8   opt-in REDUCED-PRECISION mode: 6 digits (47 fractional bits), 21 digit products.  Absolute error of the
  *                         variance ~2e-11 sigma^2 at n = 2000, i.e. NOT within 1e-9 relative where the variance is below ~1e-2 sigma^2.
+ *   BOPL_POSTERIOR_INT8_AUTO  the 6-digit split where it is safe: every bopl_set_model / bopl_fit_model first builds the 6-digit images and
+ *                         probes the model where an absolute error hurts most — up to 256 training points, every hyper-sample,
+ *                         noiseless variance against the fp64 kernel, |v6 - v64| <= 1e-9 |v64| + 64 ulp(sigma^2) — and builds the
+ *                         7-digit images instead when the probe fails (bopl_get_posterior_kernel then reports INT8_7).
  * Select BEFORE bopl_set_model / bopl_fit_model (the digit images of the factor are built at upload); switching to FP64 is
- * always allowed.  Environment default: BOPL_POSTERIOR=int8x7|fp64|int8. */
+ * always allowed.  Environment default: BOPL_POSTERIOR=int8x7|fp64|int8|int8auto. */
 #define BOPL_POSTERIOR_FP64 0
 #define BOPL_POSTERIOR_INT8 6
 #define BOPL_POSTERIOR_INT8_7 7
+#define BOPL_POSTERIOR_INT8_AUTO 60
 int bopl_set_posterior_kernel(bopl_handle* h, int kind);
 int bopl_get_posterior_kernel(const bopl_handle* h);
 
