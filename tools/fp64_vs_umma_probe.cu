@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(288, 1) probe(int mma_reps, int fp_iters, int 
   __shared__ unsigned long long bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (128 + 256) * 128 / 4; i += 288) ((uint32_t*)smem)[i] = 0x01010101u * (i & 3);
+  for (int i = tid; i < (128 + 256) * 128 / 4; i += 288) { uint32_t x = (uint32_t)i * 2654435761u + 12345u; x ^= x << 13; x ^= x >> 17; x ^= x << 5; ((uint32_t*)smem)[i] = x; }   // pseudo-random operand bytes
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -60,11 +60,29 @@ __global__ void __launch_bounds__(288, 1) probe(int mma_reps, int fp_iters, int 
       for (int it = 0; it < fp_iters; ++it)
 #pragma unroll
         for (int u = 0; u < 8; ++u) a[u] = fma(a[u], x, y);
-    } else {
+    } else if (fp_mode == 1) {
       for (int it = 0; it < fp_iters; ++it)
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(a[2 * u]), "+d"(a[2 * u + 1]) : "d"(x), "d"(y));
+    } else if (fp_mode == 2) {      // FP32 pipe: eight FFMA chains (round 2: does the FP32 pipe time-share with the int8 MMA as the FP64 pipe does?)
+      float f[8], fx = 1.0f + 1e-7f * tid, fy = 1e-7f * warp;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = (float)u;
+      for (int it = 0; it < fp_iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = fmaf(f[u], fx, fy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = f[u];
+    } else {                        // integer pipe: eight IMAD chains
+      int q[8], qx = 3 + tid, qy = warp;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = u;
+      for (int it = 0; it < fp_iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = q[u] * qx + qy;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = q[u];
     }
     const long long t1 = clock64();
     double s = 0;
@@ -89,11 +107,11 @@ int main() {
   std::vector<long long> h(sms * 2);
   printf("{\"sms\": %d", sms);
   const int reps = 20000, iters = 60000;
-  for (int fp_mode = 0; fp_mode < 2; ++fp_mode) {
-    const int it = fp_mode == 0 ? iters : iters / 2;
+  for (int fp_mode = 0; fp_mode < 4; ++fp_mode) {
+    const int it = fp_mode == 1 ? iters / 2 : iters;
     for (int cfg = 0; cfg < 3; ++cfg) {
       const int mr = (cfg == 0) ? 0 : reps, fi = (cfg == 1) ? 0 : it;
-      if (fp_mode == 1 && cfg == 1) continue;
+      if (fp_mode >= 1 && cfg == 1) continue;
       for (int rep = 0; rep < 2; ++rep) {
         CK(cudaMemset(d, 0, sms * 16 + 16 * 8));
         probe<<<sms, 288, sm>>>(mr, fi, fp_mode, d, d + sms * 2);
@@ -103,9 +121,9 @@ int main() {
       double cm = 0, cf = 0;
       for (int s = 0; s < sms; ++s) { cm += h[2 * s]; cf += h[2 * s + 1]; }
       cm /= sms; cf /= sms;
-      const char* nm = fp_mode == 0 ? "dfma" : "dmma";
+      const char* nm = fp_mode == 0 ? "dfma" : fp_mode == 1 ? "dmma" : fp_mode == 2 ? "ffma" : "imad";
       if (mr) printf(", \"%s_cfg%d_mma_mac_per_clk\": %.0f", nm, cfg, 4.0 * reps * 128 * 256 * 32 / cm);
-      if (fi) printf(", \"%s_cfg%d_fp64_fma_lanes_per_clk\": %.1f", nm, cfg, fp_mode == 0 ? 8.0 * 32 * 8 * fi / cf : 8.0 * 4 * 256 * fi / cf);
+      if (fi) printf(", \"%s_cfg%d_%s_lanes_per_clk\": %.1f", nm, cfg, fp_mode < 2 ? "fp64_fma" : "fma", fp_mode == 1 ? 8.0 * 4 * 256 * fi / cf : 8.0 * 32 * 8 * fi / cf);
       if (fi) {   // clocks of the eight FP64 warps of CTA 0 (warp w sits on sub-partition w % 4; warp 0 issues the MMAs)
         long long pw[16];
         CK(cudaMemcpy(pw, d + sms * 2, sizeof(pw), cudaMemcpyDeviceToHost));
